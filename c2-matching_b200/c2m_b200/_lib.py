@@ -1,0 +1,61 @@
+"""ctypes binding of libc2m_sm100.so (the C ABI declared in include/c2m_sm100.h).
+
+No fallback: if the library is missing or a call fails, this raises."""
+import ctypes
+import os
+
+from .build import LIB_PATH
+
+_lib = None
+
+c_f32p = ctypes.c_void_p
+c_i64p = ctypes.c_void_p
+
+
+class DcnShape(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in
+                ('B', 'C', 'H', 'W', 'Cout', 'kh', 'kw', 'sh', 'sw', 'ph', 'pw', 'dh', 'dw', 'dg')] + \
+               [(n, ctypes.c_longlong) for n in
+                ('xs_b', 'xs_c', 'xs_y', 'xs_x', 'os_b', 'os_c', 'os_y', 'os_x')]
+
+
+SYMBOLS = {
+    'c2m_abi_version': (ctypes.c_int, []),
+    'c2m_last_error': (ctypes.c_char_p, []),
+    'c2m_launch_count': (ctypes.c_ulonglong, []),
+    'c2m_corr_workspace_bytes': (ctypes.c_size_t, [ctypes.c_int] * 9),
+    'c2m_corr_argmax_f32': (ctypes.c_int, [c_f32p, c_f32p] + [ctypes.c_int] * 12 + [ctypes.c_uint, c_i64p, c_f32p,
+                                                                                 ctypes.c_void_p, ctypes.c_size_t,
+                                                                                 ctypes.c_void_p]),
+    'c2m_offset_pyramid_f32': (ctypes.c_int, [c_i64p] + [ctypes.c_int] * 5 + [c_f32p, ctypes.c_void_p]),
+    'c2m_dcn_v2_forward_f32': (ctypes.c_int, [c_f32p] * 6 + [ctypes.POINTER(DcnShape), ctypes.c_void_p]),
+    'c2m_dcn_v2_fused_forward_f32': (ctypes.c_int, [c_f32p, c_f32p, c_f32p, c_i64p] + [ctypes.c_int] * 4 +
+                                     [c_f32p, c_f32p, ctypes.c_float, c_f32p, ctypes.POINTER(DcnShape),
+                                      ctypes.c_void_p]),
+}
+
+
+class C2MError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise C2MError(
+                f'{LIB_PATH} not built: run `python -c "import __graft_entry__ as g; g.build()"` '
+                '(no CPU/PyTorch fallback exists for the B200 hot path)')
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(l, name)          # AttributeError if the .so does not export it
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().c2m_last_error().decode(errors='replace')
+        raise C2MError(f'{what} failed (status {rc}): {msg}')

@@ -1,0 +1,176 @@
+"""Torch-facing wrappers over the C ABI.  Inputs must be CUDA fp32 tensors; outputs are
+allocated here with torch (caller-owned in ABI terms) and raw pointers + the current stream
+are handed to the library."""
+import torch
+
+from . import _lib
+from ._lib import C2MError, DcnShape
+
+_ws_cache = {}
+
+
+def _require_cuda(name, t, dtype=torch.float32):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f'{name} must be a Tensor')
+    if not t.is_cuda:
+        # reference: AT_ERROR("Not implemented on the CPU") — DCNv2/src/dcn_v2.h:38
+        raise RuntimeError(f'{name} must be a CUDA tensor (Not implemented on the CPU)')
+    if t.dtype != dtype:
+        raise RuntimeError(f'{name} must be {dtype}, got {t.dtype}')
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count():
+    return int(_lib.lib().c2m_launch_count())
+
+
+def _workspace(nbytes, device):
+    """Per-(device, stream) scratch, grown on demand.  Re-entrant across DataParallel threads:
+    each replica runs on its own device."""
+    key = (device.index, _stream())
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def corr_argmax(feat_in, feat_ref, patch_size=3, input_stride=1, ref_stride=1, is_norm=True,
+                norm_input=False, l2norm=False, force_generic=False):
+    """Batched correlation + argmax.  feat_in [B,C,h,w], feat_ref [B,C,hr,wr] ->
+    (idx int64 [B,h',w'], val fp32 [B,h',w']).  See include/c2m_sm100.h."""
+    _require_cuda('feat_input', feat_in)
+    _require_cuda('feat_ref', feat_ref)
+    if feat_in.dim() != 4 or feat_ref.dim() != 4:
+        raise RuntimeError('corr_argmax expects [B,C,h,w] tensors')
+    if feat_in.shape[:2] != feat_ref.shape[:2]:
+        raise RuntimeError(f'batch/channel mismatch: {tuple(feat_in.shape)} vs {tuple(feat_ref.shape)}')
+    feat_in = feat_in.contiguous()
+    feat_ref = feat_ref.contiguous()
+    B, C, h, w = feat_in.shape
+    hr, wr = feat_ref.shape[2:]
+    L = _lib.lib()
+    with torch.cuda.device(feat_in.device):
+        need = L.c2m_corr_workspace_bytes(B, C, h, w, hr, wr, patch_size, input_stride, ref_stride)
+        if need == 0:
+            raise C2MError('corr_argmax: ' + L.c2m_last_error().decode())
+        ws = _workspace(need, feat_in.device)
+        gh, gw = (h - patch_size) // input_stride + 1, (w - patch_size) // input_stride + 1
+        idx = torch.empty(B, gh, gw, dtype=torch.int64, device=feat_in.device)
+        val = torch.empty(B, gh, gw, dtype=torch.float32, device=feat_in.device)
+        rc = L.c2m_corr_argmax_f32(feat_in.data_ptr(), feat_ref.data_ptr(), B, C, h, w, hr, wr, patch_size,
+                                   input_stride, ref_stride, int(is_norm), int(norm_input), int(l2norm),
+                                   1 if force_generic else 0, idx.data_ptr(), val.data_ptr(), ws.data_ptr(),
+                                   ws.numel(), _stream())
+        _lib.check(rc, 'c2m_corr_argmax_f32')
+    return idx, val
+
+
+def feature_match_index(feat_input, feat_ref, patch_size=3, input_stride=1, ref_stride=1, is_norm=True,
+                        norm_input=False):
+    """Drop-in for mmsr/models/archs/ref_map_util.py:26-86 (same signature, same return)."""
+    idx, val = corr_argmax(feat_input.unsqueeze(0), feat_ref.unsqueeze(0), patch_size, input_stride, ref_stride,
+                           is_norm, norm_input)
+    return idx[0], val[0]
+
+
+def offset_pyramid(idx, scale, ref_gw=None):
+    """idx int64 [B,gh,gw] -> pre_offset [B,9,s*(gh+2),s*(gw+2),2] (x,y)."""
+    _require_cuda('idx', idx, torch.int64)
+    idx = idx.contiguous()
+    B, gh, gw = idx.shape
+    out = torch.empty(B, 9, scale * (gh + 2), scale * (gw + 2), 2, dtype=torch.float32, device=idx.device)
+    with torch.cuda.device(idx.device):
+        rc = _lib.lib().c2m_offset_pyramid_f32(idx.data_ptr(), B, gh, gw, ref_gw or gw, scale, out.data_ptr(),
+                                               _stream())
+        _lib.check(rc, 'c2m_offset_pyramid_f32')
+    return out
+
+
+def _dense_nchw_or_nhwc(t):
+    """Accept NCHW-contiguous or channels-last storage without copying; otherwise make NCHW."""
+    if t.is_contiguous() or t.is_contiguous(memory_format=torch.channels_last):
+        return t
+    return t.contiguous()
+
+
+def _shape(x, cout, kh, kw, sh, sw, ph, pw, dh, dw, dg, out):
+    s = DcnShape()
+    s.B, s.C, s.H, s.W = x.shape
+    s.Cout = cout
+    s.kh, s.kw, s.sh, s.sw, s.ph, s.pw, s.dh, s.dw, s.dg = kh, kw, sh, sw, ph, pw, dh, dw, dg
+    s.xs_b, s.xs_c, s.xs_y, s.xs_x = x.stride()
+    s.os_b, s.os_c, s.os_y, s.os_x = out.stride()
+    return s
+
+
+def _out_hw(H, W, kh, kw, sh, sw, ph, pw, dh, dw):
+    return ((H + 2 * ph - (dh * (kh - 1) + 1)) // sh + 1, (W + 2 * pw - (dw * (kw - 1) + 1)) // sw + 1)
+
+
+def dcn_v2_forward(input, weight, bias, offset, mask, kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w,
+                   dilation_h, dilation_w, deformable_group):
+    """`_ext.dcn_v2_forward` (DCNv2/src/dcn_v2.h:9-39; call site dcn_v2.py:26-30)."""
+    for n, t in (('input', input), ('weight', weight), ('bias', bias), ('offset', offset), ('mask', mask)):
+        _require_cuda(n, t)
+    if weight.shape[2] != kernel_h or weight.shape[3] != kernel_w:
+        raise RuntimeError(f'Input shape and kernel shape wont match: ({kernel_h} x {kernel_w} vs '
+                           f'{weight.shape[2]} x {weight.shape[3]}).')
+    if input.shape[1] != weight.shape[1]:
+        raise RuntimeError(f'Input shape and kernel channels wont match: ({input.shape[1]} vs {weight.shape[1]}).')
+    x = _dense_nchw_or_nhwc(input)
+    B, C, H, W = x.shape
+    Ho, Wo = _out_hw(H, W, kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h, dilation_w)
+    T = kernel_h * kernel_w
+    if tuple(offset.shape) != (B, 2 * deformable_group * T, Ho, Wo) or tuple(mask.shape) != (B, deformable_group * T, Ho, Wo):
+        raise RuntimeError(f'offset/mask shape mismatch: {tuple(offset.shape)}, {tuple(mask.shape)} for output {Ho}x{Wo}')
+    out = torch.empty(B, weight.shape[0], Ho, Wo, dtype=torch.float32, device=x.device)
+    s = _shape(x, weight.shape[0], kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h, dilation_w,
+               deformable_group, out)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().c2m_dcn_v2_forward_f32(x.data_ptr(), offset.contiguous().data_ptr(),
+                                               mask.contiguous().data_ptr(), weight.contiguous().data_ptr(),
+                                               bias.contiguous().data_ptr(), out.data_ptr(), s, _stream())
+        _lib.check(rc, 'c2m_dcn_v2_forward_f32')
+    return out
+
+
+def dcn_v2_fused_forward(x, om, weight, bias, deformable_group, pre_offset=None, idx=None, pre_scale=1,
+                         ref_gw=None, lrelu_slope=1.0, channels_last_out=False):
+    """Tail of DCN_sep_pre_multi_offset.forward (dcn_v2.py:229-253) in one kernel: `om` is the raw
+    conv_offset_mask output.  Either `pre_offset` [B,9,H,W,2] or `idx` [B,gh,gw] (+pre_scale)."""
+    _require_cuda('x', x)
+    _require_cuda('om', om)
+    x = _dense_nchw_or_nhwc(x)
+    om = om.contiguous()
+    B, C, H, W = x.shape
+    kh, kw = weight.shape[2:]
+    Ho, Wo = _out_hw(H, W, kh, kw, 1, 1, kh // 2, kw // 2, 1, 1)
+    if tuple(om.shape) != (B, 3 * deformable_group * kh * kw, Ho, Wo):
+        raise RuntimeError(f'conv_offset_mask output has shape {tuple(om.shape)}')
+    mf = torch.channels_last if channels_last_out else torch.contiguous_format
+    out = torch.empty(B, weight.shape[0], Ho, Wo, dtype=torch.float32, device=x.device, memory_format=mf)
+    s = _shape(x, weight.shape[0], kh, kw, 1, 1, kh // 2, kw // 2, 1, 1, deformable_group, out)
+    pre_p = idx_p = None
+    gh = gw = 0
+    if pre_offset is not None:
+        _require_cuda('pre_offset', pre_offset)
+        if tuple(pre_offset.shape) != (B, kh * kw, Ho, Wo, 2):
+            raise RuntimeError(f'pre_offset has shape {tuple(pre_offset.shape)}')
+        pre_offset = pre_offset.contiguous()
+        pre_p = pre_offset.data_ptr()
+    elif idx is not None:
+        _require_cuda('idx', idx, torch.int64)
+        idx = idx.contiguous()
+        gh, gw = idx.shape[1:]
+        idx_p = idx.data_ptr()
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().c2m_dcn_v2_fused_forward_f32(
+            x.data_ptr(), om.data_ptr(), pre_p, idx_p, gh, gw, ref_gw or gw, pre_scale,
+            weight.contiguous().data_ptr(), bias.contiguous().data_ptr() if bias is not None else None,
+            float(lrelu_slope), out.data_ptr(), s, _stream())
+        _lib.check(rc, 'c2m_dcn_v2_fused_forward_f32')
+    return out

@@ -1,0 +1,378 @@
+// Correlation support kernels: layout/normalise/split prep, Ref patch norms, the generic
+// CUDA-core candidate search (any patch size / stride / channel count) and the exact rescoring
+// pass that produces the final index map.  See corr_internal.cuh for the HBM layouts.
+//
+// Reference semantics restated: mmsr/models/archs/ref_map_util.py:26-86 (feature_match_index) and
+// mmsr/models/archs/corres_generation_arch.py:56-58 (F.normalize over channels).
+#include "corr_internal.cuh"
+
+namespace c2m {
+
+// ------------------------------------------------------------------------------------------
+// amax over a whole map (all images) -> scale exponent so that |x| * 2^sexp <= 1024 (fp16-safe
+// with 5 bits of headroom below 65504 and the lo halves far above the subnormal range).
+// ------------------------------------------------------------------------------------------
+__global__ void amax_kernel(const float *__restrict__ x, size_t n, unsigned *__restrict__ out_bits) {
+    float m = 0.f;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out_bits, __float_as_uint(m));
+}
+
+__global__ void sexp_kernel(const unsigned *__restrict__ amax_bits, int *__restrict__ sexp, int slot, int l2norm) {
+    if (l2norm) { sexp[slot] = 10; return; }     // |x| <= 1 after normalisation
+    float a = __uint_as_float(amax_bits[slot]);
+    int e = 0;
+    if (a > 0.f && isfinite(a)) { frexpf(a, &e); }   // a = f * 2^e, f in [0.5,1)  =>  a <= 2^e
+    sexp[slot] = 10 - e;
+}
+
+// ------------------------------------------------------------------------------------------
+// prep: NCHW fp32 -> p32 / hi / lo / ss.   One block = 32 consecutive pixels of one image.
+// 256 threads; channel blocks of 64 go through a padded smem tile so that both the NCHW reads
+// (32 consecutive pixels of one channel) and the pixel-major writes are coalesced.
+// ------------------------------------------------------------------------------------------
+constexpr int PREP_PIX = 32;
+constexpr int PREP_CB = 64;
+
+__global__ void __launch_bounds__(256) prep_kernel(const float *__restrict__ x, int C, int Cp, int HW, int l2norm,
+                                                   const int *__restrict__ sexp_p, float *__restrict__ p32,
+                                                   __half *__restrict__ hi, __half *__restrict__ lo,
+                                                   float *__restrict__ ss) {
+    __shared__ float tile[PREP_CB][PREP_PIX + 1];
+    __shared__ float red[8][PREP_PIX];
+    __shared__ float ss_s[PREP_PIX];
+
+    const int b = blockIdx.y;
+    const int pix0 = blockIdx.x * PREP_PIX;
+    const int t = threadIdx.x;
+    const int lp = t & 31, lg = t >> 5;          // load mapping: pixel fastest
+    const float *xb = x + (size_t)b * C * HW;
+    const bool pv = pix0 + lp < HW;
+
+    // pass 1: per-pixel L2 norm over channels (F.normalize(dim=0): x / max(||x||_2, 1e-12))
+    float nrm = 1.f;
+    if (l2norm) {
+        float acc = 0.f;
+        for (int c = lg; c < C; c += 8) {
+            float v = pv ? xb[(size_t)c * HW + pix0 + lp] : 0.f;
+            acc = fmaf(v, v, acc);
+        }
+        red[lg][lp] = acc;
+        __syncthreads();
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += red[i][lp];
+        nrm = fmaxf(sqrtf(s), 1e-12f);
+    }
+    if (t < PREP_PIX) ss_s[t] = 0.f;
+    const float S = ldexpf(1.f, sexp_p ? *sexp_p : 0);
+
+    const int wp = t & 31, wq = t >> 5;          // hi/lo write mapping: pixel fastest, octet = wq
+    const int rp = t >> 3, rq = t & 7;           // p32 write mapping: 8 threads per pixel
+    float ssacc = 0.f;
+    for (int c0 = 0; c0 < Cp; c0 += PREP_CB) {
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < PREP_CB / 8; ++i) {
+            const int c = c0 + lg + i * 8;
+            float v = 0.f;
+            if (pv && c < C) {
+                v = xb[(size_t)c * HW + pix0 + lp];
+                if (l2norm) v = v / nrm;
+            }
+            tile[lg + i * 8][lp] = v;
+        }
+        __syncthreads();
+        // p32 [pix][Cp]
+        if (pix0 + rp < HW && c0 + rq * 8 < Cp) {
+            float4 a, bq;
+            a.x = tile[rq * 8 + 0][rp]; a.y = tile[rq * 8 + 1][rp]; a.z = tile[rq * 8 + 2][rp]; a.w = tile[rq * 8 + 3][rp];
+            bq.x = tile[rq * 8 + 4][rp]; bq.y = tile[rq * 8 + 5][rp]; bq.z = tile[rq * 8 + 6][rp]; bq.w = tile[rq * 8 + 7][rp];
+            float4 *dst = reinterpret_cast<float4 *>(p32 + ((size_t)b * HW + pix0 + rp) * Cp + c0 + rq * 8);
+            dst[0] = a;
+            dst[1] = bq;
+        }
+        // hi / lo [Cp/8][HW][8]
+        if (pix0 + wp < HW && c0 + wq * 8 < Cp) {
+            __align__(16) __half h8[8];
+            __align__(16) __half l8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float v = tile[wq * 8 + j][wp];
+                ssacc = fmaf(v, v, ssacc);
+                const float vs = v * S;
+                const __half hh = __float2half_rn(vs);
+                h8[j] = hh;
+                l8[j] = __float2half_rn(vs - __half2float(hh));
+            }
+            const size_t o = (((size_t)b * (Cp / 8) + (c0 / 8 + wq)) * HW + pix0 + wp) * 8;
+            *reinterpret_cast<uint4 *>(hi + o) = *reinterpret_cast<const uint4 *>(h8);
+            *reinterpret_cast<uint4 *>(lo + o) = *reinterpret_cast<const uint4 *>(l8);
+        }
+    }
+    atomicAdd(&ss_s[wp], ssacc);
+    __syncthreads();
+    if (t < PREP_PIX && pix0 + t < HW) ss[(size_t)b * HW + pix0 + t] = ss_s[t];
+}
+
+int corr_prep_launch(const float *x, int B, int C, int Cp, int HW, int l2norm, int map_slot,
+                     const CorrWorkspace &ws, float *p32, __half *hi, __half *lo, float *ss, cudaStream_t st) {
+    if (!l2norm) {
+        const size_t n = (size_t)B * C * HW;
+        int blocks = (int)((n + 1023) / 1024);
+        if (blocks > 1184) blocks = 1184;
+        amax_kernel<<<blocks, 256, 0, st>>>(x, n, ws.amax_bits + map_slot);
+        C2M_LAUNCH_CHECK("amax_kernel");
+    }
+    sexp_kernel<<<1, 1, 0, st>>>(ws.amax_bits, ws.sexp, map_slot, l2norm);
+    C2M_LAUNCH_CHECK("sexp_kernel");
+    dim3 grid(ceil_div(HW, PREP_PIX), B);
+    prep_kernel<<<grid, 256, 0, st>>>(x, C, Cp, HW, l2norm, ws.sexp + map_slot, p32, hi, lo, ss);
+    C2M_LAUNCH_CHECK("prep_kernel");
+    return C2M_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// rinv[b][r] = 1 / (sqrt(sum over the patch's pixels of ss) + 1e-5)      (ref_map_util.py:63)
+// ------------------------------------------------------------------------------------------
+__global__ void rinv_kernel(const float *__restrict__ ss, float *__restrict__ rinv, int hr, int wr, int rh, int rw,
+                            int patch, int s_ref, int is_norm) {
+    const int b = blockIdx.y;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rh * rw) return;
+    float v = 1.f;
+    if (is_norm) {
+        const int ry = (r / rw) * s_ref, rx = (r % rw) * s_ref;
+        const float *s = ss + (size_t)b * hr * wr;
+        float acc = 0.f;
+        for (int dy = 0; dy < patch; ++dy)
+            for (int dx = 0; dx < patch; ++dx) acc += s[(ry + dy) * wr + rx + dx];
+        v = 1.f / (sqrtf(acc) + 1e-5f);
+    }
+    rinv[(size_t)b * rh * rw + r] = v;
+}
+
+int corr_rinv_launch(const CorrGeom &g, const CorrWorkspace &ws, int is_norm, cudaStream_t st) {
+    dim3 grid(ceil_div(g.NR, 256), g.B);
+    rinv_kernel<<<grid, 256, 0, st>>>(ws.ss_ref, ws.rinv, g.hr, g.wr, g.rh, g.rw, g.patch, g.s_ref, is_norm);
+    C2M_LAUNCH_CHECK("rinv_kernel");
+    return C2M_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Generic candidate search on CUDA cores (fp32 FFMA): any patch size, strides, channel count.
+// Block = 64 queries x (all Ref patches of one chunk), 64x64 score tiles, 4x4 per thread,
+// K streamed 8 channels of one tap at a time.  Emits the same Candidate partials as the
+// tcgen05 search; the final answer always comes from the rescoring pass.
+// ------------------------------------------------------------------------------------------
+constexpr int GS_T = 64;
+
+__global__ void __launch_bounds__(256) search_generic_kernel(const float *__restrict__ pin, const float *__restrict__ pref,
+                                                             const float *__restrict__ rinv, Candidate *__restrict__ part,
+                                                             CorrGeom g, int nchunk) {
+    __shared__ __align__(16) float As[8][GS_T + 4];
+    __shared__ __align__(16) float Bs[8][GS_T + 4];
+    __shared__ int qpix[GS_T];
+    __shared__ int rpix[GS_T];
+    __shared__ float rsc[GS_T];
+    __shared__ Candidate red[GS_T][16];
+
+    const int b = blockIdx.z, chunk = blockIdx.y;
+    const int q0 = blockIdx.x * GS_T;
+    const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+    const float *pinb = pin + (size_t)b * g.h * g.w * g.Cp;
+    const float *prefb = pref + (size_t)b * g.hr * g.wr * g.Cp;
+    const float *rinvb = rinv + (size_t)b * g.NR;
+
+    if (t < GS_T) {
+        const int q = q0 + t;
+        qpix[t] = q < g.NQ ? ((q / g.gw) * g.s_in) * g.w + (q % g.gw) * g.s_in : -1;
+    }
+    const int per = ceil_div(ceil_div(g.NR, GS_T), nchunk) * GS_T;
+    const int r_begin = chunk * per, r_end = min(g.NR, r_begin + per);
+
+    float v1[4], v2[4];
+    int i1[4], i2[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v1[i] = v2[i] = -INFINITY; i1[i] = i2[i] = 0x7fffffff; }
+
+    const int lrow = t >> 1 & 63, lhalf = t & 1;     // loader: threads 0..127 -> A, 128..255 -> B
+    for (int r0 = r_begin; r0 < r_end; r0 += GS_T) {
+        __syncthreads();
+        if (t < GS_T) {
+            const int r = r0 + t;
+            const bool ok = r < r_end;
+            rpix[t] = ok ? ((r / g.rw) * g.s_ref) * g.wr + (r % g.rw) * g.s_ref : -1;
+            rsc[t] = ok ? rinvb[r] : 0.f;
+        }
+        __syncthreads();
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+        for (int tap = 0; tap < g.patch * g.patch; ++tap) {
+            const int dy = tap / g.patch, dx = tap % g.patch;
+            for (int c0 = 0; c0 < g.Cp; c0 += 8) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (t < 128) {
+                    const int pq = qpix[lrow];
+                    if (pq >= 0) v = *reinterpret_cast<const float4 *>(pinb + (size_t)(pq + dy * g.w + dx) * g.Cp + c0 + lhalf * 4);
+                } else {
+                    const int pr = rpix[lrow];
+                    if (pr >= 0) v = *reinterpret_cast<const float4 *>(prefb + (size_t)(pr + dy * g.wr + dx) * g.Cp + c0 + lhalf * 4);
+                }
+                __syncthreads();
+                float(*dst)[GS_T + 4] = t < 128 ? As : Bs;
+                dst[lhalf * 4 + 0][lrow] = v.x;
+                dst[lhalf * 4 + 1][lrow] = v.y;
+                dst[lhalf * 4 + 2][lrow] = v.z;
+                dst[lhalf * 4 + 3][lrow] = v.w;
+                __syncthreads();
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float4 a = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
+                    const float4 bb = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]);
+                    const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = r0 + tx * 4 + j;
+            if (r < r_end) {
+                const float sc = rsc[tx * 4 + j];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) cand_push(acc[i][j] * sc, r, v1[i], i1[i], v2[i], i2[i]);
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) red[ty * 4 + i][tx] = Candidate{v1[i], i1[i], v2[i], i2[i]};
+    __syncthreads();
+    if (t < GS_T && q0 + t < g.NQ) {
+        float a1 = -INFINITY, a2 = -INFINITY;
+        int j1 = 0x7fffffff, j2 = 0x7fffffff;
+        for (int k = 0; k < 16; ++k) {
+            const Candidate c = red[t][k];
+            if (c.i1 != 0x7fffffff) cand_push(c.v1, c.i1, a1, j1, a2, j2);
+            if (c.i2 != 0x7fffffff) cand_push(c.v2, c.i2, a1, j1, a2, j2);
+        }
+        part[((size_t)b * nchunk + chunk) * g.NQ + q0 + t] =
+            Candidate{a1, j1 == 0x7fffffff ? -1 : j1, a2, j2 == 0x7fffffff ? -1 : j2};
+    }
+}
+
+int corr_search_generic_launch(const CorrGeom &g, const CorrWorkspace &ws, cudaStream_t st) {
+    dim3 grid(ceil_div(g.NQ, GS_T), ws.nchunk, g.B);
+    search_generic_kernel<<<grid, 256, 0, st>>>(ws.p32_in, ws.p32_ref, ws.rinv, ws.part, g, ws.nchunk);
+    C2M_LAUNCH_CHECK("search_generic_kernel");
+    return C2M_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Exact rescoring: one warp per query.  Among the candidates whose approximate score is within
+// a relative 5e-4 of the best approximate score, recompute
+//     s(r) = float( sum_k double(q[k]) * double( float(ref[k] / (float(sqrt(ss_r)) + 1e-5f)) ) )
+// — the reference's arithmetic (Ref patch normalised in fp32 first, ref_map_util.py:63) with an
+// error-free accumulation — and keep the max (lowest index on ties).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(256) rescore_kernel(const float *__restrict__ pin, const float *__restrict__ pref,
+                                                      const Candidate *__restrict__ part, CorrGeom g, int nchunk,
+                                                      int is_norm, int norm_input, int64_t *__restrict__ idx,
+                                                      float *__restrict__ val) {
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int b = blockIdx.y;
+    if (q >= g.NQ) return;
+    const float *pinb = pin + (size_t)b * g.h * g.w * g.Cp;
+    const float *prefb = pref + (size_t)b * g.hr * g.wr * g.Cp;
+    const int qp = ((q / g.gw) * g.s_in) * g.w + (q % g.gw) * g.s_in;
+    const int taps = g.patch * g.patch;
+
+    // candidates: lane l < 2*nchunk holds one
+    float cv = -INFINITY;
+    int ci = -1;
+    if (lane < 2 * nchunk) {
+        const Candidate c = part[((size_t)b * nchunk + (lane >> 1)) * g.NQ + q];
+        cv = (lane & 1) ? c.v2 : c.v1;
+        ci = (lane & 1) ? c.i2 : c.i1;
+        if (ci < 0) cv = -INFINITY;
+    }
+    float vmax = cv;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    const float thr = vmax - (5e-4f * fabsf(vmax) + 1e-30f);
+    unsigned sel = __ballot_sync(0xffffffffu, ci >= 0 && cv >= thr);
+
+    // query patch norm
+    double ssq = 0.0;
+    if (norm_input) {
+        for (int tap = 0; tap < taps; ++tap) {
+            const float *row = pinb + (size_t)(qp + (tap / g.patch) * g.w + tap % g.patch) * g.Cp;
+            for (int c = lane; c < g.Cp; c += 32) ssq += (double)row[c] * (double)row[c];
+        }
+        ssq = warp_sum(ssq);
+    }
+
+    float best = -INFINITY;
+    int besti = 0x7fffffff;
+    while (sel) {
+        const int src = __ffs(sel) - 1;
+        sel &= sel - 1;
+        const int r = __shfl_sync(0xffffffffu, ci, src);
+        const int rp = ((r / g.rw) * g.s_ref) * g.wr + (r % g.rw) * g.s_ref;
+        float denom = 1.f;
+        if (is_norm) {
+            double ss = 0.0;
+            for (int tap = 0; tap < taps; ++tap) {
+                const float *row = prefb + (size_t)(rp + (tap / g.patch) * g.wr + tap % g.patch) * g.Cp;
+                for (int c = lane; c < g.Cp; c += 32) ss += (double)row[c] * (double)row[c];
+            }
+            ss = warp_sum(ss);
+            denom = (float)sqrt(ss) + 1e-5f;
+        }
+        double acc = 0.0;
+        for (int tap = 0; tap < taps; ++tap) {
+            const int dy = tap / g.patch, dx = tap % g.patch;
+            const float *rrow = prefb + (size_t)(rp + dy * g.wr + dx) * g.Cp;
+            const float *qrow = pinb + (size_t)(qp + dy * g.w + dx) * g.Cp;
+            for (int c = lane; c < g.Cp; c += 32) {
+                const float pn = is_norm ? __fdiv_rn(rrow[c], denom) : rrow[c];
+                acc += (double)qrow[c] * (double)pn;
+            }
+        }
+        acc = warp_sum(acc);
+        const float s = (float)acc;
+        if (cand_better(s, r, best, besti)) { best = s; besti = r; }
+    }
+    if (lane == 0) {
+        idx[(size_t)b * g.NQ + q] = besti == 0x7fffffff ? 0 : besti;
+        val[(size_t)b * g.NQ + q] = norm_input ? best / ((float)sqrt(ssq) + 1e-5f) : best;
+    }
+}
+
+int corr_rescore_launch(const CorrGeom &g, const CorrWorkspace &ws, int is_norm, int norm_input, int64_t *idx,
+                        float *val, cudaStream_t st) {
+    dim3 grid(ceil_div(g.NQ, 8), g.B);
+    rescore_kernel<<<grid, 256, 0, st>>>(ws.p32_in, ws.p32_ref, ws.part, g, ws.nchunk, is_norm, norm_input, idx, val);
+    C2M_LAUNCH_CHECK("rescore_kernel");
+    return C2M_OK;
+}
+
+}  // namespace c2m

@@ -1,0 +1,69 @@
+// Internal interfaces between the correlation kernels (prep -> search -> rescore).
+//
+// Data layout in HBM (per feature map of one call, all images b of the batch):
+//   p32   [B][HW][Cp]        fp32, pixel-major ("NHWC"), Cp = C rounded up to 8, pad = 0.
+//                            Exact values the search is defined on (optionally L2-normalised).
+//   hi,lo [B][Cp/8][HW][8]   fp16 split operands of x * 2^sexp:  hi = rn(x*S), lo = rn(x*S - hi).
+//                            One 16-byte element per (channel-octet, pixel): a (W*8)-wide row of
+//                            one image row is contiguous, so a TMA box of (cols*8, rows, octets)
+//                            lands in shared memory as [octet][pixel][8 halfs] = the tcgen05
+//                            K-major no-swizzle core-matrix layout with rows 16 B apart.
+//   ss    [B][HW]            fp32 per-pixel sum of squares of p32 (for the patch norms).
+//   rinv  [B][NR]            fp32 1 / (sqrt(sum_{patch} ss) + 1e-5)   (1 when !is_norm)
+//   part  [B][nchunk][NQ]    Candidate: approximate top-2 of each query over one Ref chunk.
+#pragma once
+#include "c2m_common.cuh"
+
+namespace c2m {
+
+struct __align__(16) Candidate {
+    float v1;
+    int i1;
+    float v2;
+    int i2;
+};
+
+struct CorrGeom {
+    int B, C, Cp;
+    int h, w, hr, wr;        // map sizes
+    int patch, s_in, s_ref;
+    int gh, gw, rh, rw;      // patch grids: input (gh x gw), Ref (rh x rw)
+    int NQ, NR;
+};
+
+struct CorrWorkspace {
+    float *p32_in, *p32_ref;
+    __half *hi_in, *lo_in, *hi_ref, *lo_ref;
+    float *ss_in, *ss_ref;
+    float *rinv;
+    Candidate *part;
+    unsigned *amax_bits;     // [2]
+    int *sexp;               // [2] scale exponents for (in, ref)
+    int nchunk;
+    size_t total_bytes;
+};
+
+// lexicographic "better": larger score, then lower Ref index
+__device__ __forceinline__ bool cand_better(float s, int r, float v, int i) {
+    return s > v || (s == v && r < i);
+}
+__device__ __forceinline__ void cand_push(float s, int r, float &v1, int &i1, float &v2, int &i2) {
+    if (cand_better(s, r, v1, i1)) {
+        v2 = v1; i2 = i1; v1 = s; i1 = r;
+    } else if (cand_better(s, r, v2, i2)) {
+        v2 = s; i2 = r;
+    }
+}
+
+int corr_prep_launch(const float *x, int B, int C, int Cp, int HW, int l2norm, int map_slot,
+                     const CorrWorkspace &ws, float *p32, __half *hi, __half *lo, float *ss,
+                     cudaStream_t st);
+int corr_rinv_launch(const CorrGeom &g, const CorrWorkspace &ws, int is_norm, cudaStream_t st);
+int corr_search_generic_launch(const CorrGeom &g, const CorrWorkspace &ws, cudaStream_t st);
+int corr_search_umma_launch(const CorrGeom &g, const CorrWorkspace &ws, cudaStream_t st);
+bool corr_umma_supported(const CorrGeom &g);
+int corr_umma_pick_nchunk(const CorrGeom &g);
+int corr_rescore_launch(const CorrGeom &g, const CorrWorkspace &ws, int is_norm, int norm_input,
+                        int64_t *idx, float *val, cudaStream_t st);
+
+}  // namespace c2m

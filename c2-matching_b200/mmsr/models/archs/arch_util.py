@@ -1,0 +1,62 @@
+"""Building blocks shared by the archs (reference: mmsr/models/archs/arch_util.py; only the
+pieces the restoration-forward path uses)."""
+import torch
+from torch import nn
+from torch.nn import init
+
+
+def default_init_weights(modules, scale=1.0):
+    """Kaiming-normal (fan_in) x scale, zero bias — arch_util.py:40-61."""
+    for root in modules if isinstance(modules, (list, tuple)) else [modules]:
+        for m in root.modules():
+            if isinstance(m, (nn.Conv2d, nn.Linear)):
+                init.kaiming_normal_(m.weight, a=0, mode='fan_in')
+                with torch.no_grad():
+                    m.weight.mul_(scale)
+                    if m.bias is not None:
+                        m.bias.zero_()
+
+
+def srntt_init_weights(net, init_type='normal', init_gain=0.02):
+    """N(0, gain) for every module whose class name contains Conv/Linear — arch_util.py:12-37.
+    (DCN modules do not match and keep their own uniform init, as in the reference.)"""
+    if init_type != 'normal':
+        raise NotImplementedError(f'initialization method [{init_type}] is not implemented')
+    for m in net.modules():
+        cname = type(m).__name__
+        if hasattr(m, 'weight') and ('Conv' in cname or 'Linear' in cname):
+            init.normal_(m.weight.data, 0.0, init_gain)
+            if getattr(m, 'bias', None) is not None:
+                init.constant_(m.bias.data, 0.0)
+
+
+class ResidualBlockNoBN(nn.Module):
+    """x + conv2(relu(conv1(x))) * res_scale — arch_util.py:80-136 (state-dict keys conv1/conv2)."""
+
+    def __init__(self, nf=64, res_scale=1, pytorch_init=False):
+        super().__init__()
+        self.res_scale = res_scale
+        self.conv1 = nn.Conv2d(nf, nf, 3, 1, 1, bias=True)
+        self.conv2 = nn.Conv2d(nf, nf, 3, 1, 1, bias=True)
+        if not pytorch_init:
+            default_init_weights([self.conv1, self.conv2], 0.1)
+
+    def forward(self, x):
+        y = self.conv2(torch.relu_(self.conv1(x)))
+        return x + y if self.res_scale == 1 else x + y * self.res_scale
+
+
+def make_layer(block, n_blocks, **kwargs):
+    return nn.Sequential(*[block(**kwargs) for _ in range(n_blocks)])
+
+
+def tensor_shift(x, shift=(2, 2), fill_val=0):
+    """Shift [b,h,w,c] down/right with constant fill — arch_util.py:291-315.  Kept for API
+    parity; the B200 path builds all shifted offsets in one kernel (csrc/offsets.cu)."""
+    sh, sw = shift
+    if sh < 0 or sw < 0:
+        raise NotImplementedError
+    out = torch.full_like(x, fill_val)
+    h, w = x.shape[1:3]
+    out[:, sh:, sw:, :] = x[:, :h - sh, :w - sw, :]
+    return out

@@ -1,0 +1,101 @@
+"""VGG trunks with the reference's layer names (mmsr/models/archs/vgg_arch.py:7-145).
+
+Built layer by layer here (no torchvision model object, no download at construction): only
+the convolutions up to the deepest requested layer exist, exactly like the reference's
+`features[:max_idx + 1]` slice, so state-dict keys are `vgg_net.conv{b}_{i}.{weight,bias}` plus
+the `mean` / `std` buffers.  ImageNet weights, when wanted, are loaded with `load_imagenet()`
+from a local torchvision checkpoint (the reference downloads them in the constructor)."""
+from collections import OrderedDict
+
+import torch
+from torch import nn
+
+_CFG = {  # convs per block
+    'vgg11': (1, 1, 2, 2, 2), 'vgg13': (2, 2, 2, 2, 2), 'vgg16': (2, 2, 3, 3, 3), 'vgg19': (2, 2, 4, 4, 4),
+}
+_WIDTH = (64, 128, 256, 512, 512)
+
+
+def layer_names(vgg_type):
+    """['conv1_1','relu1_1',...,'pool5'] — vgg_arch.py:7-41 NAMES."""
+    names = []
+    for b, n in enumerate(_CFG[vgg_type.replace('_bn', '')], start=1):
+        for i in range(1, n + 1):
+            names += [f'conv{b}_{i}', f'relu{b}_{i}']
+        names.append(f'pool{b}')
+    return names
+
+
+NAMES = {k: layer_names(k) for k in _CFG}
+
+
+def build_trunk(vgg_type, last_layer, pooling_stride=2, remove_pooling=False):
+    """Sequential of named layers up to and including `last_layer`."""
+    seq = OrderedDict()
+    cin = 3
+    for name in layer_names(vgg_type):
+        if name.startswith('conv'):
+            cout = _WIDTH[int(name[4]) - 1]
+            seq[name] = nn.Conv2d(cin, cout, 3, 1, 1)
+            cin = cout
+        elif name.startswith('relu'):
+            seq[name] = nn.ReLU(inplace=True)
+        elif not remove_pooling:
+            seq[name] = nn.MaxPool2d(kernel_size=2, stride=pooling_stride)
+        if name == last_layer:
+            break
+    else:
+        raise ValueError(f'{last_layer} is not a layer of {vgg_type}')
+    return nn.Sequential(seq)
+
+
+def load_imagenet(trunk, vgg_type, path=None):
+    """Copy torchvision ImageNet weights (`features.N.*`) into a named trunk.  `path`: a local
+    torchvision vgg checkpoint; if None, torchvision's cache is tried (no network here)."""
+    if path is not None:
+        tv = torch.load(path, map_location='cpu')
+    else:
+        import torchvision
+        tv = getattr(torchvision.models, vgg_type)(weights='IMAGENET1K_V1').state_dict()
+    convs = [m for m in trunk if isinstance(m, nn.Conv2d)]
+    keys = sorted({int(k.split('.')[1]) for k in tv if k.startswith('features.')})
+    for m, n in zip(convs, keys):
+        m.weight.data.copy_(tv[f'features.{n}.weight'])
+        m.bias.data.copy_(tv[f'features.{n}.bias'])
+
+
+class VGGFeatureExtractor(nn.Module):
+    """Returns {layer_name: feature} for the requested layers — vgg_arch.py:59-145."""
+
+    def __init__(self, layer_name_list, vgg_type='vgg19', use_input_norm=True, requires_grad=False,
+                 remove_pooling=False, pooling_stride=2, pretrained_path=None):
+        super().__init__()
+        if 'bn' in vgg_type:
+            raise NotImplementedError('batch-norm VGG variants are not used by C2-Matching')
+        self.layer_name_list = list(layer_name_list)
+        self.use_input_norm = use_input_norm
+        self.names = layer_names(vgg_type)
+        last = max(self.layer_name_list, key=self.names.index)
+        self.vgg_net = build_trunk(vgg_type, last, pooling_stride, remove_pooling)
+        if pretrained_path is not None:
+            load_imagenet(self.vgg_net, vgg_type, pretrained_path)
+        if not requires_grad:
+            for p in self.parameters():
+                p.requires_grad = False
+        if use_input_norm:
+            self.register_buffer('mean', torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1))
+            self.register_buffer('std', torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1))
+
+    def forward(self, x):
+        if self.use_input_norm:
+            x = (x - self.mean) / self.std
+        out = {}
+        for name, layer in self.vgg_net.named_children():
+            if isinstance(layer, nn.ReLU) and name in self.layer_name_list:
+                x = torch.relu(x)          # out-of-place: the tapped tensor must survive
+                out[name] = x
+                continue
+            x = layer(x)
+            if name in self.layer_name_list:
+                out[name] = x.clone() if not isinstance(layer, nn.ReLU) else x
+        return out

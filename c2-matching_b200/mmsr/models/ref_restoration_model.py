@@ -1,0 +1,123 @@
+"""Inference-side `RefRestorationModel` (reference: mmsr/models/ref_restoration_model.py,
+base_model.py, sr_model.py): owns net_extractor / net_map / net_g, loads the reference's
+checkpoints strictly, `feed_data` / `test` / `get_current_visuals` / `validation`.
+
+Execution differences from the reference: one process per GPU instead of
+nn.DataParallel; no per-image `torch.cuda.empty_cache()`; validation can be rank-sharded with
+`torch.distributed` (the reference's dist validation is broken, sr_model.py:160-162) and metrics
+are all-gathered at the end.  Training methods are out of scope and raise."""
+import logging
+import os
+import os.path as osp
+from collections import OrderedDict
+
+import torch
+
+from c2m_b200.dist import gather_rows
+from mmsr.models import networks
+from mmsr.utils import metrics
+from mmsr.utils.util import tensor2img
+
+logger = logging.getLogger('base')
+
+
+class RefRestorationModel:
+
+    def __init__(self, opt):
+        self.opt = opt
+        if opt.get('is_train'):
+            raise NotImplementedError('the B200 build covers inference (restoration forward) only')
+        self.is_train = False
+        if not torch.cuda.is_available():
+            raise RuntimeError('RefRestorationModel needs a CUDA device: the B200 hot path has no CPU fallback')
+        self.device = torch.device('cuda', torch.cuda.current_device())
+        self.net_g = networks.define_net_g(opt).to(self.device).eval()
+        self.net_map = networks.define_net_map(opt).to(self.device).eval()
+        self.net_extractor = networks.define_net_extractor(opt).to(self.device).eval()
+        path = opt.get('path') or {}
+        strict = path.get('strict_load', True)
+        if path.get('pretrain_model_feature_extractor'):
+            self.load_network(self.net_extractor, path['pretrain_model_feature_extractor'], strict)
+        if path.get('pretrain_model_g'):
+            self.load_network(self.net_g, path['pretrain_model_g'], strict)
+
+    # -- checkpoint I/O (base_model.py:245-265: strips DataParallel's `module.` prefix)
+    def load_network(self, net, load_path, strict=True):
+        logger.info(f'Loading {net.__class__.__name__} model from {load_path}.')
+        sd = torch.load(load_path, map_location='cpu')
+        sd = OrderedDict((k[7:] if k.startswith('module.') else k, v) for k, v in sd.items())
+        net.load_state_dict(sd, strict=strict)
+
+    def save_network(self, net, net_label, current_iter):
+        save_path = osp.join(self.opt['path']['models'], f'{net_label}_{current_iter}.pth')
+        torch.save(OrderedDict((k, v.cpu()) for k, v in net.state_dict().items()), save_path)
+
+    # -- data / forward (ref_restoration_model.py:186-190, 271-287)
+    def feed_data(self, data):
+        nb = dict(non_blocking=True)
+        self.img_in_lq = data['img_in_lq'].to(self.device, **nb)
+        self.img_ref = data['img_ref'].to(self.device, **nb)
+        if 'img_in' in data:
+            self.gt = data['img_in'].to(self.device, **nb)
+        self.match_img_in = data['img_in_up'].to(self.device, **nb)
+
+    @torch.no_grad()
+    def test(self):
+        self.features = self.net_extractor(self.match_img_in, self.img_ref)
+        self.pre_offset, self.img_ref_feat = self.net_map(self.features, self.img_ref)
+        self.output = self.net_g(self.img_in_lq, self.pre_offset, self.img_ref_feat)
+
+    def get_current_visuals(self):
+        out = OrderedDict(img_in_lq=self.img_in_lq.detach().cpu(), rlt=self.output.detach().cpu())
+        if hasattr(self, 'gt'):
+            out['gt'] = self.gt.detach().cpu()
+        return out
+
+    def optimize_parameters(self, step):
+        raise NotImplementedError('training is outside the B200 hot-path scope')
+
+    # -- validation (ref_restoration_model.py:295-370), optionally rank-sharded
+    def validation(self, dataloader, current_iter, tb_logger=None, save_img=False):
+        dist_on = torch.distributed.is_available() and torch.distributed.is_initialized()
+        rank = torch.distributed.get_rank() if dist_on else 0
+        world = torch.distributed.get_world_size() if dist_on else 1
+        crop = self.opt.get('crop_border')
+        if crop is None:
+            crop = self.opt.get('scale', 4)
+        rows = []
+        dataset_name = dataloader.dataset.opt['name']
+        for i, val_data in enumerate(dataloader):
+            if i % world != rank:
+                continue
+            img_name = osp.splitext(osp.basename(val_data['lq_path'][0]))[0]
+            self.feed_data(val_data)
+            self.test()
+            visuals = self.get_current_visuals()
+            sr_img, gt_img = tensor2img([visuals['rlt'], visuals['gt']])
+            if val_data.get('padding') is not None and bool(val_data['padding']):
+                oh, ow = [int(v) for v in val_data['original_size'][:2]]
+                sr_img = sr_img[:oh, :ow]
+                gt_img = gt_img[:oh, :ow]
+            if save_img:
+                import cv2
+                out_dir = osp.join(self.opt['path']['visualization'], dataset_name)
+                os.makedirs(out_dir, exist_ok=True)
+                name = f"{img_name}_{self.opt['name']}" + (f"_{self.opt['suffix']}" if self.opt.get('suffix') else '')
+                cv2.imwrite(osp.join(out_dir, name + '.png'), sr_img)
+            psnr = metrics.psnr(sr_img, gt_img, crop_border=crop)
+            sr_y = metrics.bgr2ycbcr(sr_img / 255., only_y=True)
+            gt_y = metrics.bgr2ycbcr(gt_img / 255., only_y=True)
+            psnr_y = metrics.psnr(sr_y * 255, gt_y * 255, crop_border=crop)
+            ssim_y = metrics.ssim(sr_y * 255, gt_y * 255, crop_border=crop)
+            rows.append((i, psnr, psnr_y, ssim_y))
+            logger.info(f'# img {img_name} # PSNR: {psnr:.4e} # PSNR_Y: {psnr_y:.4e} # SSIM_Y: {ssim_y:.4e}.')
+        t = torch.tensor(rows, dtype=torch.float64, device=self.device).reshape(-1, 4)
+        t = gather_rows(t)
+        avg = t[:, 1:].mean(0).tolist() if t.numel() else [float('nan')] * 3
+        if rank == 0:
+            logger.info(f'# Validation {dataset_name} # PSNR: {avg[0]:.4e} # PSNR_Y: {avg[1]:.4e} # SSIM_Y: {avg[2]:.4e}.')
+            if tb_logger:
+                for k, v in zip(('psnr', 'psnr_y', 'ssim_y'), avg):
+                    tb_logger.add_scalar(k, v, current_iter)
+        self.last_validation = {'psnr': avg[0], 'psnr_y': avg[1], 'ssim_y': avg[2], 'n': int(t.shape[0])}
+        return self.last_validation

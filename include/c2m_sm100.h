@@ -1,0 +1,117 @@
+/*
+ * libc2m_sm100 — C ABI of the B200-native C2-Matching restoration-forward hot path.
+ *
+ * Plain C: raw device pointers, sizes, a CUDA stream handle, int status.  No torch / ATen
+ * types.  Every entry point is asynchronous on `stream`, re-entrant (no global scratch: the
+ * caller owns outputs and the workspace) and takes the device from the current CUDA context,
+ * which is what the reference's operator boundary assumes (it launches on the current stream
+ * of the tensors' device under the GIL, DCNv2/src/cuda/dcn_v2_cuda.cu:107,139).
+ *
+ * Reference interfaces replaced (paths relative to the reference repo root):
+ *   c2m_dcn_v2_forward_f32          <- `_ext.dcn_v2_forward`
+ *                                      mmsr/models/archs/DCNv2/src/vision.cpp:3-8 (pybind export),
+ *                                      src/dcn_v2.h:9-39 (dispatch), src/cuda/dcn_v2_cuda.cu:42-172
+ *   c2m_dcn_v2_fused_forward_f32    <- DCN_sep_pre_multi_offset.forward (everything after the
+ *                                      conv_offset_mask conv) mmsr/models/archs/DCNv2/dcn_v2.py:229-253
+ *   c2m_corr_argmax_f32             <- feature_match_index  mmsr/models/archs/ref_map_util.py:26-86
+ *                                      (+ optional fused per-pixel channel L2 normalisation,
+ *                                      mmsr/models/archs/corres_generation_arch.py:56-58)
+ *   c2m_offset_pyramid_f32          <- index_to_flow + 9-shift x scale pyramid
+ *                                      mmsr/models/archs/corres_generation_arch.py:29-46,70-104
+ *
+ * The Python binding a reference maintainer would add is shown in INTEGRATION.md.
+ */
+#ifndef C2M_SM100_H
+#define C2M_SM100_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* same object as cudaStream_t / CUstream */
+typedef struct CUstream_st *c2m_stream_t;
+
+/* status codes (0 = ok).  c2m_last_error() returns a thread-local description. */
+enum {
+    C2M_OK = 0,
+    C2M_ERR_INVALID = 1,      /* bad shape / argument (reference: AT_ASSERTM -> RuntimeError) */
+    C2M_ERR_WORKSPACE = 2,    /* workspace missing or too small */
+    C2M_ERR_CUDA = 3,         /* CUDA runtime / launch failure (reference only printf'd these) */
+    C2M_ERR_UNSUPPORTED = 4   /* no sm_100 device / driver entry point missing */
+};
+
+int c2m_abi_version(void);
+const char *c2m_last_error(void);
+
+/* --- correlation / index_map --------------------------------------------------------------
+ * For b in [0,B):  idx[b,q] = argmax_r < P_in(b,q), P_ref(b,r) / (||P_ref(b,r)|| + 1e-5) >
+ * over the Ref patch grid (lowest r on ties), val[b,q] = that maximum (divided by
+ * ||P_in(b,q)|| + 1e-5 when norm_input).  fin [B,C,h,w], fref [B,C,hr,wr] fp32 NCHW;
+ * idx int64 [B,h',w'], val fp32 [B,h',w'], h' = (h-patch)/s_in+1.  B = 1 is the reference call.
+ *
+ * l2norm != 0 first applies x[:,p] / max(||x[:,p]||, 1e-12) to both maps (the caller's
+ * F.normalize in the reference).
+ *
+ * flags: bit0 = force the generic CUDA-core search instead of the tcgen05 kernel.
+ * The tcgen05 search proposes candidates; the returned idx/val always come from the exact
+ * (double-accumulated, float-rounded) rescoring pass, so they do not depend on tensor-core
+ * rounding.
+ */
+size_t c2m_corr_workspace_bytes(int B, int C, int h, int w, int hr, int wr, int patch, int s_in, int s_ref);
+
+int c2m_corr_argmax_f32(const float *fin, const float *fref, int B, int C, int h, int w, int hr, int wr,
+                        int patch, int s_in, int s_ref, int is_norm, int norm_input, int l2norm,
+                        unsigned flags, int64_t *idx, float *val, void *ws, size_t ws_bytes,
+                        c2m_stream_t stream);
+
+/* --- idx -> pre-offset pyramid ------------------------------------------------------------
+ * idx [B,gh,gw] -> out [B,9,s*(gh+2),s*(gw+2),2] fp32, last dim (x,y);  tap k=3i+j is the flow
+ * map scaled by s, nearest-upsampled by s and shifted down/right by (s*i, s*j), zero filled.
+ * ref_gw: patch-grid width used to decode idx (the reference uses gw, the INPUT grid width).
+ */
+int c2m_offset_pyramid_f32(const int64_t *idx, int B, int gh, int gw, int ref_gw, int scale, float *out,
+                           c2m_stream_t stream);
+
+/* --- modulated deformable convolution v2, forward -----------------------------------------
+ * out[b,o,p] = bias[o] + sum_{c,i,j} W[o,c,i,j] * mask[b,g(c)*kh*kw+i*kw+j,p] *
+ *              bilinear(x[b,c], ho*sh-ph+i*dh+off_y, wo*sw-pw+j*dw+off_x)
+ * off_y/off_x = offset[b, 2*(g*kh*kw+i*kw+j) (+1), p];  sample is 0 unless
+ * -1 < y < H and -1 < x < W; g(c) = c / (C/dg).   All tensors fp32.
+ * x  : [B,C,H,W]; element (b,c,y,x) at x[b*xs_b + c*xs_c + y*xs_y + x*xs_x]  (element strides,
+ *      so NCHW-contiguous and channels-last storage are both accepted)
+ * out: [B,Cout,Ho,Wo]; element strides os_b, os_c, os_y, os_x likewise.
+ * offset [B,2*dg*kh*kw,Ho,Wo], mask [B,dg*kh*kw,Ho,Wo], weight [Cout,C,kh,kw], bias [Cout] or NULL:
+ * contiguous.
+ */
+typedef struct {
+    int B, C, H, W, Cout;
+    int kh, kw, sh, sw, ph, pw, dh, dw, dg;
+    long long xs_b, xs_c, xs_y, xs_x;
+    long long os_b, os_c, os_y, os_x;
+} c2m_dcn_shape;
+
+int c2m_dcn_v2_forward_f32(const float *x, const float *offset, const float *mask, const float *weight,
+                           const float *bias, float *out, const c2m_dcn_shape *shape, c2m_stream_t stream);
+
+/* Fused DCN_sep_pre_multi_offset tail: `om` = conv_offset_mask(feat) [B,3*dg*kh*kw,Ho,Wo] raw;
+ *   off_y = om[2j] + pre[...,1], off_x = om[2j+1] + pre[...,0], mask = sigmoid(om[2*dg*kh*kw + j]),
+ *   j = g*kh*kw + k;  pre = pre_offset [B,kh*kw,Ho,Wo,2] (x,y) or NULL.
+ * If pre == NULL and idx != NULL the pre-offsets are rebuilt on the fly from idx [B,gh,gw]
+ * (pyramid scale `pre_scale`, decode width ref_gw) exactly as c2m_offset_pyramid_f32 would.
+ * lrelu_slope: out = v > 0 ? v : slope*v applied when lrelu_slope != 1 (pass 1.f for none).
+ */
+int c2m_dcn_v2_fused_forward_f32(const float *x, const float *om, const float *pre, const int64_t *idx,
+                                 int gh, int gw, int ref_gw, int pre_scale, const float *weight,
+                                 const float *bias, float lrelu_slope, float *out,
+                                 const c2m_dcn_shape *shape, c2m_stream_t stream);
+
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+unsigned long long c2m_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* C2M_SM100_H */

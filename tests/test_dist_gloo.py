@@ -1,0 +1,51 @@
+"""world_size-2 gloo (CPU) test of the multi-GPU host logic: pair sharding `rank::world`, the
+ragged metric gather and the max-over-ranks timing reduction (c2m_b200/dist.py)."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, n_pairs, q):
+    sys.path.insert(0, os.path.join(ROOT, 'c2-matching_b200'))
+    from c2m_b200.dist import gather_rows, max_over_ranks, shard_indices
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    mine = shard_indices(n_pairs, rank, world)
+    rows = torch.tensor([[i, 30.0 + i, 0.5] for i in mine], dtype=torch.float64).reshape(-1, 3)
+    allrows = gather_rows(rows)
+    tmax = max_over_ranks(1.0 + rank, 'cpu')
+    if rank == 0:
+        q.put((allrows.tolist(), tmax))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_and_gather_world2():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    n_pairs, world, port = 7, 2, 29531 + os.getpid() % 200
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_pairs, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    rows, tmax = q.get(timeout=120)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert sorted(int(r[0]) for r in rows) == list(range(n_pairs))       # every pair exactly once
+    assert [int(r[0]) for r in rows] == [0, 2, 4, 6, 1, 3, 5]           # rank order, ragged (4 + 3)
+    assert all(abs(r[1] - (30.0 + r[0])) < 1e-12 for r in rows)
+    assert tmax == 2.0
+
+
+def test_shard_indices_cover():
+    sys.path.insert(0, os.path.join(ROOT, 'c2-matching_b200'))
+    from c2m_b200.dist import shard_indices
+    for n in (0, 1, 126):
+        for w in (1, 2, 4, 8):
+            got = sorted(i for r in range(w) for i in shard_indices(n, r, w))
+            assert got == list(range(n))

@@ -1,0 +1,151 @@
+"""Diagnostic run on the GPU box: every kernel vs the oracle, mismatch statistics printed (no
+asserts) so one gpurun call tells as much as possible.  Not a test, not a benchmark."""
+import os
+import sys
+import time
+import traceback
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, 'c2-matching_b200'), os.path.join(ROOT, 'tests', 'golden')):
+    sys.path.insert(0, p)
+import make_golden as mg  # noqa: E402
+import seeding  # noqa: E402
+from oracle import c_oracle, ref_path  # noqa: E402
+import c2m_b200 as c2m  # noqa: E402
+
+dev = torch.device('cuda:0')
+G = {n: np.load(os.path.join(ROOT, 'tests', 'golden', n + '.npz')) for n in ('corr', 'offsets', 'dcn', 'full')}
+
+
+def section(name):
+    print(f'\n===== {name} =====', flush=True)
+
+
+def corr_diag():
+    section('corr vs golden')
+    for case in mg.CORR_CASES:
+        name = case[0]
+        fin, fref = mg.corr_inputs(case)
+        ref_idx = G['corr'][f'{name}/ni1/idx']
+        ref_val = G['corr'][f'{name}/ni1/val']
+        for force in (True, False):
+            try:
+                idx, val = c2m.corr_argmax(fin[None].to(dev), fref[None].to(dev), is_norm=True, norm_input=True,
+                                           force_generic=force)
+                torch.cuda.synchronize()
+                idx = idx[0].cpu().numpy()
+                val = val[0].cpu().numpy()
+                bad = int((idx != ref_idx).sum())
+                dv = float(np.abs(val - ref_val).max())
+                print(f'{name:14s} generic={force!s:5s} idx mismatches {bad}/{idx.size}  max|dval| {dv:.3e}', flush=True)
+                if bad and bad < 20:
+                    ys, xs = np.nonzero(idx != ref_idx)
+                    for y, x in list(zip(ys, xs))[:5]:
+                        print(f'    q=({y},{x}) got {idx[y, x]} want {ref_idx[y, x]} val {val[y, x]:.6f} vs {ref_val[y, x]:.6f}')
+            except Exception:
+                traceback.print_exc()
+
+
+def corr_big():
+    section('corr big (160x160 maps, 256ch) umma vs generic, timing')
+    for (B, h, hr) in ((1, 40, 125), (1, 160, 160), (4, 160, 160)):
+        fin = torch.stack([seeding.unit_features(900 + b, 256, h, h) for b in range(B)]).to(dev)
+        fref = torch.stack([seeding.unit_features(950 + b, 256, hr, hr) for b in range(B)]).to(dev)
+        res = {}
+        for force in (False, True):
+            if force and B > 1:
+                continue
+            try:
+                for it in range(3):
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    idx, val = c2m.corr_argmax(fin, fref, is_norm=True, norm_input=True, force_generic=force)
+                    torch.cuda.synchronize()
+                    dt = time.perf_counter() - t0
+                res[force] = (idx.cpu(), val.cpu())
+                nq = idx[0].numel()
+                nr = (hr - 2) ** 2
+                fl = 2 * 2304 * nq * nr * B
+                print(f'B={B} {h}x{h} vs {hr}x{hr} generic={force}: {dt * 1e3:.2f} ms  ({fl / dt / 1e12:.1f} TFLOP/s algorithmic)', flush=True)
+            except Exception:
+                traceback.print_exc()
+        if True in res and False in res:
+            bad = int((res[True][0] != res[False][0]).sum())
+            print(f'   umma vs generic idx mismatches: {bad}; max|dval| {float((res[True][1] - res[False][1]).abs().max()):.3e}')
+        if h <= 40 and False in res:
+            t0 = time.perf_counter()
+            oi, ov = ref_path.feature_match_index(fin[0].cpu(), fref[0].cpu(), 3, 1, 1, True, True)
+            print(f'   torch-cpu oracle {time.perf_counter() - t0:.2f}s; idx mismatches vs oracle: {int((oi != res[False][0][0]).sum())}')
+
+
+def offsets_diag():
+    section('offset pyramid')
+    idx = torch.randint(0, 12 * 14, (2, 12, 14), dtype=torch.int64)
+    for s in (1, 2, 4):
+        got = c2m.offset_pyramid(idx.to(dev), s).cpu()
+        want = torch.stack([c_oracle.offset_pyramid(idx[b], s) for b in range(2)])
+        print(f'scale {s}: equal={torch.equal(got, want)}')
+
+
+def dcn_diag():
+    section('dcn vs literal C oracle / golden')
+    import _ext
+    for case in mg.DCN_CASES:
+        name, b, c, cout, h, w, dg, seed, osc = case
+        x = seeding.randn(seed, (b, c, h, w))
+        wgt = seeding.randn(seed + 5, (cout, c, 3, 3), 0.1)
+        bias = seeding.randn(seed + 6, (cout,))
+        off = seeding.randn(seed + 7, (b, 2 * dg * 9, h, w), 2.0 * osc)
+        off[:, :, ::2, ::3] = off[:, :, ::2, ::3].round()
+        mask = torch.sigmoid(seeding.randn(seed + 8, (b, dg * 9, h, w)))
+        want = c_oracle.dcn_v2_forward(x, wgt, bias, off, mask, dg=dg, acc64=True)
+        try:
+            got = _ext.dcn_v2_forward(x.to(dev), wgt.to(dev), bias.to(dev), off.to(dev), mask.to(dev), 3, 3, 1, 1, 1, 1, 1, 1, dg).cpu()
+            print(f'{name}: _ext max abs err {float((got - want).abs().max()):.3e} (out rms {float(want.pow(2).mean().sqrt()):.3f})')
+            got = _ext.dcn_v2_forward(x.to(dev).contiguous(memory_format=torch.channels_last), wgt.to(dev), bias.to(dev), off.to(dev), mask.to(dev), 3, 3, 1, 1, 1, 1, 1, 1, dg).cpu()
+            print(f'{name}: _ext(channels_last x) max abs err {float((got - want).abs().max()):.3e}')
+        except Exception:
+            traceback.print_exc()
+    # timing at BASELINE config 4 and the three full-size layers
+    section('dcn timing')
+    for (C, H, B) in ((64, 160, 1), (256, 160, 1), (128, 320, 1), (64, 640, 1)):
+        x = torch.randn(B, C, H, H, device=dev)
+        wgt = torch.randn(C, C, 3, 3, device=dev) * 0.05
+        bias = torch.randn(C, device=dev)
+        off = torch.randn(B, 144, H, H, device=dev) * 3
+        mask = torch.sigmoid(torch.randn(B, 72, H, H, device=dev))
+        import torchvision
+        for tag, fn in (('c2m', lambda: _ext.dcn_v2_forward(x, wgt, bias, off, mask, 3, 3, 1, 1, 1, 1, 1, 1, 8)),
+                        ('c2m-nhwc', lambda: _ext.dcn_v2_forward(x.contiguous(memory_format=torch.channels_last), wgt, bias, off, mask, 3, 3, 1, 1, 1, 1, 1, 1, 8)),
+                        ('torchvision', lambda: torchvision.ops.deform_conv2d(x, off, wgt, bias, padding=1, mask=mask))):
+            try:
+                for _ in range(2):
+                    y = fn()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(5):
+                    y = fn()
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / 5
+                print(f'C={C} H={H}: {tag:12s} {ms:.3f} ms  ({2 * C * C * 9 * H * H / ms / 1e9:.1f} TFLOP/s)', flush=True)
+            except Exception:
+                traceback.print_exc()
+
+
+if __name__ == '__main__':
+    print(torch.cuda.get_device_name(0), torch.__version__)
+    c_oracle.build()
+    which = sys.argv[1:] or ['corr', 'big', 'offsets', 'dcn']
+    if 'corr' in which:
+        corr_diag()
+    if 'offsets' in which:
+        offsets_diag()
+    if 'dcn' in which:
+        dcn_diag()
+    if 'big' in which:
+        corr_big()
