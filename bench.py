@@ -1,0 +1,274 @@
+#!/usr/bin/env python
+"""Benchmark of the C2-Matching restoration-forward hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    (N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...)
+
+Metric (BASELINE.json): SR images/s, LR 160x160 -> 640x640 with a 500x500 Ref (zero-padded to
+640x640, as the reference dataset does).  A step = one full forward (extractor -> correlation /
+index_map -> offsets -> restoration net with 3 fused DCNs) over a batch of 4 synthetic pairs per
+GPU (BASELINE config 2), random-init weights of the real architecture.  Weak scaling: each rank
+processes its own batch, no data-path collective; `value` = images of all ranks / max-over-ranks
+time.
+
+One JSON line on rank 0 (see the task contract): value (inputs resident in HBM), e2e (host
+pinned inputs -> H2D -> forward -> D2H of the SR images, through the public
+RestorationPipeline.run_host call), roofline of the dominant kernel (the tcgen05 correlation
+search, timed live with CUDA events on its own stream by the library's profiling hook),
+cpu_baseline (the oracle port of the reference's CPU path on this box's host cores, bounded
+sample), clocks, gpu_launches.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, 'c2-matching_b200'), os.path.join(ROOT, 'tests', 'golden')):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+LR, REF, BATCH, CH = 160, 500, 4, 256
+WORKLOAD = 'config2: LR 160x160 -> SR 640x640, Ref 500x500 zero-padded to 640x640, batch 4 per GPU'
+
+
+# ------------------------------------------------------------------------------- helpers
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_ev = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_ev.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-i',
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.splitlines()[0].split(',')])
+            except Exception:
+                pass
+            self._stop_ev.wait(0.2)
+
+    def stop(self):
+        self._stop_ev.set()
+        self.join(timeout=5)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[3:7]) if v.lower().startswith('active')})
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(self.rows)}
+
+
+def seeded_weights():
+    import seeding
+    return (seeding.share_extractor_weights(seeding.seeded_state_dict(seeding.spec_extractor(), 11)),
+            seeding.seeded_state_dict(seeding.spec_net_map(), 12),
+            seeding.seeded_state_dict(seeding.spec_restoration_net(), 13))
+
+
+def corr_algorithmic(batch):
+    """per image FLOPs = 2*C*p^2*N_in*N_ref, bytes = 4*C*(HW_in+HW_ref) + 12*N_in."""
+    n = (LR - 2) ** 2
+    flops = 2.0 * CH * 9 * n * n * batch
+    byts = (4.0 * CH * (LR * LR * 2) + 12.0 * n) * batch
+    return flops, byts
+
+
+def cpu_baseline(sample_images=1, threads=None):
+    """The reference's CPU path (oracle port, kind "port": the reference is Python and
+    /root/reference does not exist on the GPU box) on a bounded sample of the same workload."""
+    import seeding  # noqa: F401
+    from c2m_b200.pipeline import synthetic_pair
+    from oracle import ref_path
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sd_e, sd_m, sd_g = seeded_weights()
+    img_lq, img_up, img_ref = synthetic_pair(1234, sample_images, LR, REF)
+    t0 = time.perf_counter()
+    ref_path.full_forward(sd_e, sd_m, sd_g, img_lq, img_up, img_ref)
+    dt = time.perf_counter() - t0
+    return {'value': sample_images / dt, 'unit': 'images/s', 'cores': threads, 'kind': 'port',
+            'sample': f'{sample_images} image(s) of the workload, full forward, fp32 torch-CPU oracle port '
+                      f'(oracle/ref_path.py), {dt:.1f} s'}
+
+
+# ------------------------------------------------------------------------------- reference arm
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    from c2m_b200.pipeline import synthetic_pair
+    from oracle import ref_path
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sd_e, sd_m, sd_g = seeded_weights()
+    img_lq, img_up, img_ref = synthetic_pair(1234, 1, LR, REF)     # bounded sample: 1 image per step
+    budget_s = 200.0
+    t_est = None
+    for _ in range(max(1, min(args.warmup, 1))):
+        t0 = time.perf_counter()
+        ref_path.full_forward(sd_e, sd_m, sd_g, img_lq, img_up, img_ref)
+        t_est = time.perf_counter() - t0
+    steps = max(1, min(args.steps, int(budget_s / max(t_est, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ref_path.full_forward(sd_e, sd_m, sd_g, img_lq, img_up, img_ref)
+    dt = time.perf_counter() - t0
+    v = steps / dt
+    sample = (f'1 image per step (config-2 shapes), {steps} timed steps of {args.steps} requested, '
+              f'torch-CPU oracle port of the reference path, {threads} threads')
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'SR images/sec (160x160->640x640, 500x500 Ref)', 'value': v, 'unit': 'images/s',
+        'n_gpus': args.gpus, 'steps': steps, 'warmup': 1, 'ms_per_step': dt / steps * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'reference_arm': 'CPU, batch 1 per step'},
+        'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': threads, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }), flush=True)
+
+
+# ------------------------------------------------------------------------------- our arm
+def run_ours(args, rank, world, local_rank):
+    import c2m_b200 as c2m
+    from c2m_b200 import ops
+    from c2m_b200.dist import max_over_ranks
+    from c2m_b200.pipeline import RestorationPipeline, synthetic_pair
+    import __graft_entry__ as entry
+    entry.build()
+
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    dist_on = world > 1
+    if dist_on:
+        torch.distributed.init_process_group('nccl', device_id=dev)
+    pipe = RestorationPipeline(dev, allow_tf32=bool(args.tf32), channels_last=bool(args.channels_last))
+    pipe.load_state_dicts(*seeded_weights()).place()
+
+    img_lq, img_up, img_ref = synthetic_pair(1234 + rank * 1000, BATCH, LR, REF)
+    host = [t.pin_memory() for t in (img_lq, img_up, img_ref)]
+    devt = [t.to(dev) for t in host]
+    out_host = torch.empty(BATCH, 3, 4 * LR, 4 * LR, dtype=torch.float32).pin_memory()
+    flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    h2d = sum(t.numel() * t.element_size() for t in host)
+    d2h = out_host.numel() * out_host.element_size()
+
+    def barrier():
+        if dist_on:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        """K steps, each bracketed by events on the current stream, L2 flushed (untimed) between them."""
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        for e0, e1 in evs:
+            flush.fill_(1)
+            e0.record()
+            fn()
+            e1.record()
+        barrier()
+        ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+        return max_over_ranks(ms, dev)
+
+    step_dev = lambda: pipe.forward(*devt)
+    step_e2e = lambda: pipe.run_host(*host, out=out_host)
+
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    step_e2e()
+    torch.cuda.synchronize(dev)
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ops.profile_enable(True)
+    ops.profile_corr_search_ms()
+    n0 = c2m.launch_count()
+    ms_dev = timed(step_dev, args.steps)
+    launches = c2m.launch_count() - n0
+    search_ms, search_n = ops.profile_corr_search_ms()
+    ops.profile_enable(False)
+    clocks = sampler.stop() if sampler else None
+    ms_e2e = timed(step_e2e, args.steps)
+
+    imgs = BATCH * args.steps * world
+    value = imgs / (ms_dev / 1e3)
+    e2e = imgs / (ms_e2e / 1e3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        peak = peaks.get('bf16_tflops_sustained')       # kernel timed inside a long step -> sustained figure
+        peak_src = 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)'
+        if not peak:
+            peak, peak_src = 1400.0, 'fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained)'
+        flops, byts = corr_algorithmic(BATCH)
+        per_launch_s = search_ms / max(search_n, 1) / 1e3
+        achieved = flops / per_launch_s / 1e12
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'corr_umma_traffic.json'))).get('dram_bytes_per_launch')
+        except Exception:
+            pass
+        roofline = {'bound': 'tensor', 'kernel': 'corr_umma_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
+                    'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+                    'ms_per_launch': per_launch_s * 1e3, 'algorithmic_flops_per_launch': flops,
+                    'algorithmic_bytes_per_launch': byts,
+                    'issued_mma_flops_per_launch': 3 * flops * (160 * 160 / (158. * 158.)) ** 2,
+                    'hbm_gbps_at_algorithmic_bytes': byts / per_launch_s / 1e9,
+                    'note': '3 fp16 MMAs per K step (hi*hi+hi*lo+lo*hi) for fp32-grade scores: tensor-pipe busy '
+                            'fraction is ~3x the algorithmic fraction'}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_baseline(1)
+        print(json.dumps({
+            'metric': 'SR images/sec (160x160->640x640, 500x500 Ref)', 'value': value, 'unit': 'images/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32' if not args.tf32 else 'f32 (cuDNN convs TF32)', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'global_batch': BATCH * world, 'parallelism': f'dp{world} (batch-sharded pairs, no data-path collective)',
+                       'l2': 'flushed between timed steps (192 MiB fill)', 'weights': 'random-init (seeded), real architecture',
+                       'convs': 'cuDNN fp32' + (' TF32' if args.tf32 else ''), 'channels_last': bool(args.channels_last)},
+            'e2e': {'value': e2e, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'ms_per_step': ms_e2e / args.steps, 'api': 'c2m_b200.pipeline.RestorationPipeline.run_host'},
+            'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu, 'clocks': clocks,
+        }), flush=True)
+    if dist_on:
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', choices=['ours', 'reference'], default='ours')
+    ap.add_argument('--tf32', type=int, default=0, help='allow cuDNN TF32 for the plain convolutions (default: exact fp32)')
+    ap.add_argument('--channels-last', type=int, default=0)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference':
+        run_reference(args, rank)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == '__main__':
+    main()

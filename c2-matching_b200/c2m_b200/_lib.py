@@ -23,6 +23,8 @@ SYMBOLS = {
     'c2m_abi_version': (ctypes.c_int, []),
     'c2m_last_error': (ctypes.c_char_p, []),
     'c2m_launch_count': (ctypes.c_ulonglong, []),
+    'c2m_profile_enable': (ctypes.c_int, [ctypes.c_int]),
+    'c2m_profile_corr_search_ms': (ctypes.c_int, [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)]),
     'c2m_corr_workspace_bytes': (ctypes.c_size_t, [ctypes.c_int] * 9),
     'c2m_corr_argmax_f32': (ctypes.c_int, [c_f32p, c_f32p] + [ctypes.c_int] * 12 + [ctypes.c_uint, c_i64p, c_f32p,
                                                                                  ctypes.c_void_p, ctypes.c_size_t,

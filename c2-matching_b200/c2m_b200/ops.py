@@ -27,6 +27,18 @@ def launch_count():
     return int(_lib.lib().c2m_launch_count())
 
 
+def profile_enable(on=True):
+    _lib.check(_lib.lib().c2m_profile_enable(int(bool(on))), 'c2m_profile_enable')
+
+
+def profile_corr_search_ms():
+    """(total device ms, launches) of the correlation search kernel since the last query."""
+    import ctypes
+    ms, n = ctypes.c_float(0), ctypes.c_int(0)
+    _lib.check(_lib.lib().c2m_profile_corr_search_ms(ctypes.byref(ms), ctypes.byref(n)), 'c2m_profile_corr_search_ms')
+    return float(ms.value), int(n.value)
+
+
 def _workspace(nbytes, device):
     """Per-(device, stream) scratch, grown on demand.  Re-entrant across DataParallel threads:
     each replica runs on its own device."""

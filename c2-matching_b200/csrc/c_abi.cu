@@ -3,6 +3,8 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstring>
+#include <mutex>
+#include <vector>
 
 #include "corr_internal.cuh"
 
@@ -18,6 +20,10 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static std::atomic<int> g_profile{0};
+static std::mutex g_prof_mu;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
 
 static int make_geom(CorrGeom &g, int B, int C, int h, int w, int hr, int wr, int patch, int s_in, int s_ref) {
     C2M_CHECK_ARG(B > 0 && C > 0, "corr: empty batch or channels (B=%d C=%d)", B, C);
@@ -112,7 +118,44 @@ extern "C" int c2m_corr_argmax_f32(const float *fin, const float *fref, int B, i
     if ((rc = corr_prep_launch(fin, B, C, g.Cp, h * w, l2norm, 0, ws, ws.p32_in, ws.hi_in, ws.lo_in, ws.ss_in, st))) return rc;
     if ((rc = corr_prep_launch(fref, B, C, g.Cp, hr * wr, l2norm, 1, ws, ws.p32_ref, ws.hi_ref, ws.lo_ref, ws.ss_ref, st))) return rc;
     if ((rc = corr_rinv_launch(g, ws, is_norm, st))) return rc;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    const bool prof = g_profile.load() != 0;
+    if (prof) {
+        C2M_CUDA(cudaEventCreate(&e0));
+        C2M_CUDA(cudaEventCreate(&e1));
+        C2M_CUDA(cudaEventRecord(e0, st));
+    }
     rc = use_umma ? corr_search_umma_launch(g, ws, st) : corr_search_generic_launch(g, ws, st);
     if (rc) return rc;
+    if (prof) {
+        C2M_CUDA(cudaEventRecord(e1, st));
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        g_prof_events.emplace_back(e0, e1);
+    }
     return corr_rescore_launch(g, ws, is_norm, norm_input, idx, val, st);
+}
+
+extern "C" int c2m_profile_enable(int on) {
+    g_profile.store(on ? 1 : 0);
+    return C2M_OK;
+}
+
+extern "C" int c2m_profile_corr_search_ms(float *ms_total, int *launches) {
+    C2M_CHECK_ARG(ms_total && launches, "profile: null pointer");
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    float total = 0.f;
+    int n = 0;
+    for (auto &pr : g_prof_events) {
+        C2M_CUDA(cudaEventSynchronize(pr.second));
+        float ms = 0.f;
+        C2M_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        total += ms;
+        ++n;
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    g_prof_events.clear();
+    *ms_total = total;
+    *launches = n;
+    return C2M_OK;
 }

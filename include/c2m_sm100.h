@@ -111,6 +111,13 @@ int c2m_dcn_v2_fused_forward_f32(const float *x, const float *om, const float *p
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 unsigned long long c2m_launch_count(void);
 
+/* Measurement hook (bench.py `roofline`): while enabled, every c2m_corr_argmax_f32 call brackets
+ * its candidate-search kernel (the dominant kernel of the path) with CUDA events on the caller's
+ * stream.  c2m_profile_corr_search_ms synchronises those events, returns the summed device time
+ * in *ms_total and the number of search launches in *launches, and clears the list. */
+int c2m_profile_enable(int on);
+int c2m_profile_corr_search_ms(float *ms_total, int *launches);
+
 #ifdef __cplusplus
 }
 #endif

