@@ -23,6 +23,16 @@ SYMBOLS = {
     'c2m_abi_version': (ctypes.c_int, []),
     'c2m_last_error': (ctypes.c_char_p, []),
     'c2m_launch_count': (ctypes.c_ulonglong, []),
+    'c2m_conv3x3_packed_weight_bytes': (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
+    'c2m_conv3x3_supported': (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
+    'c2m_conv3x3_pack_weights_f32': (ctypes.c_int, [c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    'c2m_psa_from_f32': (ctypes.c_int, [c_f32p] + [ctypes.c_int] * 4 + [ctypes.c_longlong] * 4 +
+                         [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    'c2m_psa_to_f32': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 5 + [c_f32p, c_f32p] +
+                       [ctypes.c_longlong] * 4 + [ctypes.c_void_p]),
+    'c2m_conv3x3_psa': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 5 +
+                        [ctypes.c_void_p, c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                         ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     'c2m_profile_enable': (ctypes.c_int, [ctypes.c_int]),
     'c2m_profile_corr_search_ms': (ctypes.c_int, [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)]),
     'c2m_corr_workspace_bytes': (ctypes.c_size_t, [ctypes.c_int] * 9),

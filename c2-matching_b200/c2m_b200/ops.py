@@ -186,3 +186,100 @@ def dcn_v2_fused_forward(x, om, weight, bias, deformable_group, pre_offset=None,
             float(lrelu_slope), out.data_ptr(), s, _stream())
         _lib.check(rc, 'c2m_dcn_v2_fused_forward_f32')
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Packed-split activations ("PSA") and the tcgen05 3x3 convolution (include/c2m_sm100.h)
+class PSA:
+    """fp16 hi/lo planes [B][ceil(C/8)][H][W][8]; value = (hi + lo) * 2^-sa."""
+    __slots__ = ('hi', 'lo', 'B', 'C', 'H', 'W', 'sa')
+
+    def __init__(self, hi, lo, B, C, H, W, sa=0):
+        self.hi, self.lo, self.B, self.C, self.H, self.W, self.sa = hi, lo, B, C, H, W, sa
+
+    @staticmethod
+    def empty(B, C, H, W, device, sa=0):
+        c8 = (C + 7) // 8
+        buf = torch.empty(2, B, c8, H, W, 8, dtype=torch.float16, device=device)
+        return PSA(buf[0], buf[1], B, C, H, W, sa)
+
+    @property
+    def shape(self):
+        return (self.B, self.C, self.H, self.W)
+
+
+def psa_from_f32(x, sa=0):
+    _require_cuda('x', x)
+    B, C, H, W = x.shape
+    out = PSA.empty(B, C, H, W, x.device, sa)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().c2m_psa_from_f32(x.data_ptr(), B, C, H, W, *x.stride(), sa, out.hi.data_ptr(),
+                                         out.lo.data_ptr(), _stream())
+        _lib.check(rc, 'c2m_psa_from_f32')
+    return out
+
+
+def psa_to_f32(p, add=None, channels_last=False):
+    mf = torch.channels_last if channels_last else torch.contiguous_format
+    out = torch.empty(p.B, p.C, p.H, p.W, dtype=torch.float32, device=p.hi.device, memory_format=mf)
+    if add is not None:
+        _require_cuda('add', add)
+        if add.shape != out.shape or add.stride() != out.stride():
+            add = add.contiguous(memory_format=mf)
+    with torch.cuda.device(out.device):
+        rc = _lib.lib().c2m_psa_to_f32(p.hi.data_ptr(), p.lo.data_ptr(), p.B, p.C, p.H, p.W, p.sa,
+                                       add.data_ptr() if add is not None else None, out.data_ptr(), *out.stride(),
+                                       _stream())
+        _lib.check(rc, 'c2m_psa_to_f32')
+    return out
+
+
+def conv3x3_supported(cin, cout, H=None, W=None):
+    ok = bool(_lib.lib().c2m_conv3x3_supported(cin, cout))
+    if H is not None:
+        ok = ok and H >= 18 and W >= 10
+    return ok
+
+
+_wpack_cache = {}
+
+
+def conv3x3_pack_weights(weight):
+    """Pack (and cache per parameter version) a [Cout,Cin,3,3] fp32 weight for c2m_conv3x3_psa."""
+    _require_cuda('weight', weight)
+    key = (weight.data_ptr(), weight._version, tuple(weight.shape), weight.device.index)
+    blob = _wpack_cache.get(key)
+    if blob is None:
+        cout, cin = weight.shape[:2]
+        n = _lib.lib().c2m_conv3x3_packed_weight_bytes(cin, cout)
+        blob = torch.empty(n, dtype=torch.uint8, device=weight.device)
+        with torch.cuda.device(weight.device):
+            rc = _lib.lib().c2m_conv3x3_pack_weights_f32(weight.contiguous().data_ptr(), cin, cout, blob.data_ptr(),
+                                                         _stream())
+            _lib.check(rc, 'c2m_conv3x3_pack_weights_f32')
+        if len(_wpack_cache) > 4096:
+            _wpack_cache.clear()
+        _wpack_cache[key] = blob
+    return blob
+
+
+_ACT = {None: 0, 'none': 0, 'relu': 1, 'lrelu': 2}
+
+
+def conv3x3_psa(x, weight, bias, act=None, residual=None, out=None, sa_out=0):
+    """out = act(conv3x3(x, weight) + bias) + residual, all PSA (fp32-grade, tensor cores)."""
+    cout, cin = weight.shape[:2]
+    if cin != x.C:
+        raise RuntimeError(f'conv3x3_psa: weight expects {cin} input channels, got {x.C}')
+    blob = conv3x3_pack_weights(weight)
+    if out is None:
+        out = PSA.empty(x.B, cout, x.H, x.W, x.hi.device, sa_out)
+    with torch.cuda.device(x.hi.device):
+        rc = _lib.lib().c2m_conv3x3_psa(
+            x.hi.data_ptr(), x.lo.data_ptr(), x.B, cin, x.H, x.W, x.sa, blob.data_ptr(),
+            bias.data_ptr() if bias is not None else None, cout, _ACT[act],
+            residual.hi.data_ptr() if residual is not None else None,
+            residual.lo.data_ptr() if residual is not None else None, residual.sa if residual is not None else 0,
+            out.hi.data_ptr(), out.lo.data_ptr(), out.sa, _stream())
+        _lib.check(rc, 'c2m_conv3x3_psa')
+    return out

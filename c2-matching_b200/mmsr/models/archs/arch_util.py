@@ -46,6 +46,50 @@ class ResidualBlockNoBN(nn.Module):
         return x + y if self.res_scale == 1 else x + y * self.res_scale
 
 
+def fast_conv_enabled():
+    """C2M_FAST_CONV=0 routes every plain convolution back to cuDNN (debug / A-B comparisons)."""
+    import os
+    return os.environ.get('C2M_FAST_CONV', '1') != '0'
+
+
+def psa_conv_ok(conv, H, W):
+    """True if `conv` (3x3, stride 1, pad 1) can run on the tcgen05 kernel for an HxW map."""
+    from c2m_b200 import ops
+    return (fast_conv_enabled() and isinstance(conv, nn.Conv2d) and conv.kernel_size == (3, 3) and
+            conv.stride == (1, 1) and conv.padding == (1, 1) and conv.dilation == (1, 1) and conv.groups == 1 and
+            conv.weight.is_cuda and not torch.is_grad_enabled() and
+            ops.conv3x3_supported(conv.in_channels, conv.out_channels, H, W))
+
+
+def resblocks_psa(body, hp):
+    """Run a Sequential of ResidualBlockNoBN on a packed-split activation (PSA) with the tcgen05
+    3x3 kernel: x + conv2(relu(conv1(x))) per block, two launches per block, no fp32 round trip.
+    Three PSA buffers are cycled."""
+    from c2m_b200 import ops
+    bufs = [hp, ops.PSA.empty(hp.B, hp.C, hp.H, hp.W, hp.hi.device), ops.PSA.empty(hp.B, hp.C, hp.H, hp.W, hp.hi.device)]
+    cur = 0
+    for blk in body:
+        t, nxt = bufs[(cur + 1) % 3], bufs[(cur + 2) % 3]
+        ops.conv3x3_psa(bufs[cur], blk.conv1.weight, blk.conv1.bias, act='relu', out=t)
+        res = bufs[cur]
+        if blk.res_scale != 1:
+            raise NotImplementedError('res_scale != 1 is not used by C2-Matching')
+        ops.conv3x3_psa(t, blk.conv2.weight, blk.conv2.bias, act=None, residual=res, out=nxt)
+        cur = (cur + 2) % 3
+    return bufs[cur]
+
+
+def body_forward(body, h, skip=None):
+    """body(h) (+ skip): tcgen05 path when supported, else the plain modules."""
+    from c2m_b200 import ops
+    blk0 = body[0]
+    if h.is_cuda and all(isinstance(b, ResidualBlockNoBN) for b in body) and psa_conv_ok(blk0.conv1, h.shape[2], h.shape[3]):
+        out = resblocks_psa(body, ops.psa_from_f32(h))
+        return ops.psa_to_f32(out, add=skip)
+    y = body(h)
+    return y if skip is None else y + skip
+
+
 def make_layer(block, n_blocks, **kwargs):
     return nn.Sequential(*[block(**kwargs) for _ in range(n_blocks)])
 

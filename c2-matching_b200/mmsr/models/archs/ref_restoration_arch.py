@@ -26,6 +26,11 @@ class ContentExtractor(nn.Module):
         arch_util.default_init_weights([self.conv_first], 0.1)
 
     def forward(self, x):
+        from c2m_b200 import ops
+        if x.is_cuda and arch_util.psa_conv_ok(self.conv_first, x.shape[2], x.shape[3]) and \
+                arch_util.psa_conv_ok(self.body[0].conv1, x.shape[2], x.shape[3]):
+            hp = ops.conv3x3_psa(ops.psa_from_f32(x), self.conv_first.weight, self.conv_first.bias, act='lrelu')
+            return ops.psa_to_f32(arch_util.resblocks_psa(self.body, hp))
         return self.body(F.leaky_relu(self.conv_first(x), 0.1))
 
 
@@ -54,9 +59,18 @@ class DynamicAggregationRestoration(nn.Module):
             pre = pre_offset.handle(key) if hasattr(pre_offset, 'handle') else pre_offset[key]
             swapped = getattr(self, f'{size}_dyn_agg')([ref, off], pre, lrelu_slope=0.1)   # lrelu fused
             h = getattr(self, f'head_{size}')(torch.cat([x, swapped], 1))
-            h = getattr(self, f'body_{size}')(h) + x
-            x = getattr(self, f'tail_{size}')(h)
+            h = arch_util.body_forward(getattr(self, f'body_{size}'), h, skip=x)
+            x = self._tail(size, h)
         return x
+
+    def _tail(self, size, h):
+        tail = getattr(self, f'tail_{size}')
+        if size == 'large' and h.is_cuda and arch_util.psa_conv_ok(tail[0], h.shape[2], h.shape[3]) and \
+                arch_util.psa_conv_ok(tail[2], h.shape[2], h.shape[3]):
+            from c2m_b200 import ops
+            t = ops.conv3x3_psa(ops.psa_from_f32(h), tail[0].weight, tail[0].bias, act='lrelu')
+            return ops.psa_to_f32(ops.conv3x3_psa(t, tail[2].weight, tail[2].bias))
+        return tail(h)
 
 
 class RestorationNet(nn.Module):

@@ -325,3 +325,42 @@ def test_cli_runs_on_synthetic_yaml(tmp_path):
                        timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     assert '# Validation synth # PSNR:' in r.stderr + r.stdout
+
+
+# ------------------------------------------------------------------------------- tcgen05 3x3 conv
+@pytest.mark.parametrize('cfg', [(2, 64, 64, 40, 44, 'relu', False), (1, 64, 64, 37, 29, None, True),
+                                 (1, 64, 32, 32, 32, 'lrelu', False), (1, 32, 3, 48, 40, None, False),
+                                 (2, 3, 64, 32, 24, 'lrelu', False), (1, 24, 40, 33, 21, 'relu', True)],
+                         ids=lambda c: f'{c[1]}to{c[2]}_{c[3]}x{c[4]}')
+def test_conv3x3_psa_vs_fp64(cfg):
+    """Split-fp16 tensor-core convolution: fp32-grade (<= 1e-5 of the output scale, i.e. at least as
+    close to the fp64 result as cuDNN's fp32 kernels), incl. ragged tiles, padded channel counts,
+    fused activation and residual."""
+    from c2m_b200 import ops
+    B, cin, cout, H, W, act, res = cfg
+    x = seeding.randn(1, (B, cin, H, W), 1.5)
+    w = seeding.randn(2, (cout, cin, 3, 3), 0.05)
+    b = seeding.randn(3, (cout,), 0.5)
+    r = seeding.randn(4, (B, cout, H, W)) if res else None
+    want = F.conv2d(x.double(), w.double(), b.double(), 1, 1)
+    want = want.relu() if act == 'relu' else F.leaky_relu(want, 0.1) if act == 'lrelu' else want
+    if res:
+        want = want + r.double()
+    xp = ops.psa_from_f32(x.to(DEV))
+    assert float((ops.psa_to_f32(xp).cpu() - x).abs().max()) <= 2e-6 * 1.5 * 5      # 22-bit split
+    yp = ops.conv3x3_psa(xp, w.to(DEV), b.to(DEV), act=act, residual=ops.psa_from_f32(r.to(DEV)) if res else None)
+    got = ops.psa_to_f32(yp, channels_last=True)
+    assert got.is_contiguous(memory_format=torch.channels_last)
+    err = float((got.cpu().double() - want).abs().max())
+    assert err <= 1e-5 * float(want.abs().max()), err
+
+
+def test_resblock_chain_fast_path_equals_module_path():
+    from mmsr.models.archs import arch_util
+    body = arch_util.make_layer(arch_util.ResidualBlockNoBN, 4, nf=64).to(DEV).eval()
+    h = seeding.randn(9, (2, 64, 36, 28)).to(DEV)
+    skip = seeding.randn(10, (2, 64, 36, 28)).to(DEV)
+    with torch.no_grad():
+        fast = arch_util.body_forward(body, h, skip=skip)
+        slow = body(h) + skip
+    _rel_ok(fast, slow, 2e-5)

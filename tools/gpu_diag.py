@@ -137,10 +137,78 @@ def dcn_diag():
                 traceback.print_exc()
 
 
+def conv_diag():
+    section('conv3x3 tcgen05 (fp16x3) vs fp64 reference')
+    import torch.nn.functional as F
+    from c2m_b200 import ops
+    for (B, cin, cout, H, W, act, res) in ((2, 64, 64, 40, 44, 'relu', False), (1, 64, 64, 37, 29, None, True),
+                                           (1, 64, 32, 32, 32, 'lrelu', False), (1, 32, 3, 48, 40, None, False),
+                                           (2, 3, 64, 32, 24, 'lrelu', False), (1, 24, 40, 33, 21, 'relu', True)):
+        try:
+            x = seeding.randn(1, (B, cin, H, W), 1.5)
+            w = seeding.randn(2, (cout, cin, 3, 3), 0.05)
+            b = seeding.randn(3, (cout,), 0.5)
+            r = seeding.randn(4, (B, cout, H, W)) if res else None
+            want = F.conv2d(x.double(), w.double(), b.double(), 1, 1)
+            if act == 'relu':
+                want = want.relu()
+            elif act == 'lrelu':
+                want = F.leaky_relu(want, 0.1)
+            if res:
+                want = want + r.double()
+            xp = ops.psa_from_f32(x.to(dev))
+            back = ops.psa_to_f32(xp).cpu()
+            rp = ops.psa_from_f32(r.to(dev)) if res else None
+            yp = ops.conv3x3_psa(xp, w.to(dev), b.to(dev), act=act, residual=rp)
+            got = ops.psa_to_f32(yp).cpu()
+            torch.cuda.synchronize()
+            torch.backends.cudnn.allow_tf32 = False
+            cud = F.conv2d(x.to(dev), w.to(dev), b.to(dev), 1, 1).cpu()
+            print(f'B{B} {cin}->{cout} {H}x{W} act={act} res={res}: psa roundtrip err {float((back - x).abs().max()):.2e}; '
+                  f'conv max err {float((got.double() - want).abs().max()):.3e} (scale {float(want.abs().max()):.2f}); '
+                  f'[cuDNN fp32 pre-act err {float((cud.double() - F.conv2d(x.double(), w.double(), b.double(), 1, 1)).abs().max()):.3e}]', flush=True)
+        except Exception:
+            traceback.print_exc()
+    section('conv3x3 timing, 64->64, B=4')
+    for H in (160, 320, 640):
+        x = torch.randn(4, 64, H, H, device=dev)
+        w = torch.randn(64, 64, 3, 3, device=dev) * 0.05
+        b = torch.randn(64, device=dev)
+        xp = ops.psa_from_f32(x)
+        yp = ops.PSA.empty(4, 64, H, H, dev)
+
+        def t(fn, n=10):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / n
+        try:
+            ms = t(lambda: ops.conv3x3_psa(xp, w, b, act='relu', out=yp))
+            ms_r = t(lambda: ops.conv3x3_psa(xp, w, b, act=None, residual=xp, out=yp))
+            torch.backends.cudnn.allow_tf32 = False
+            ms_c = t(lambda: F.conv2d(x, w, b, 1, 1), 5)
+            torch.backends.cudnn.allow_tf32 = True
+            ms_t = t(lambda: F.conv2d(x, w, b, 1, 1), 5)
+            torch.backends.cudnn.allow_tf32 = False
+            ms_cv = t(lambda: ops.psa_from_f32(x))
+            fl = 2 * 64 * 64 * 9 * H * H * 4
+            print(f'H={H}: c2m {ms:.3f} ms ({fl / ms / 1e9:.0f} TFLOP/s alg), +residual {ms_r:.3f} ms; cuDNN fp32 {ms_c:.3f} ms; cuDNN tf32 {ms_t:.3f} ms; psa_from_f32 {ms_cv:.3f} ms', flush=True)
+        except Exception:
+            traceback.print_exc()
+
+
 if __name__ == '__main__':
     print(torch.cuda.get_device_name(0), torch.__version__)
     c_oracle.build()
     which = sys.argv[1:] or ['corr', 'big', 'offsets', 'dcn']
+    if 'conv' in which:
+        conv_diag()
     if 'corr' in which:
         corr_diag()
     if 'offsets' in which:
