@@ -241,25 +241,26 @@ def conv3x3_supported(cin, cout, H=None, W=None):
     return ok
 
 
-_wpack_cache = {}
-
-
 def conv3x3_pack_weights(weight):
-    """Pack (and cache per parameter version) a [Cout,Cin,3,3] fp32 weight for c2m_conv3x3_psa."""
+    """Pack a [Cout,Cin,3,3] fp32 weight for c2m_conv3x3_psa.  The blob is cached ON the tensor
+    object (so it dies with it — a global cache keyed by data_ptr would alias a freed parameter's
+    address) and re-made when the storage or the version counter changes."""
     _require_cuda('weight', weight)
-    key = (weight.data_ptr(), weight._version, tuple(weight.shape), weight.device.index)
-    blob = _wpack_cache.get(key)
-    if blob is None:
-        cout, cin = weight.shape[:2]
-        n = _lib.lib().c2m_conv3x3_packed_weight_bytes(cin, cout)
-        blob = torch.empty(n, dtype=torch.uint8, device=weight.device)
-        with torch.cuda.device(weight.device):
-            rc = _lib.lib().c2m_conv3x3_pack_weights_f32(weight.contiguous().data_ptr(), cin, cout, blob.data_ptr(),
-                                                         _stream())
-            _lib.check(rc, 'c2m_conv3x3_pack_weights_f32')
-        if len(_wpack_cache) > 4096:
-            _wpack_cache.clear()
-        _wpack_cache[key] = blob
+    tag = (weight.data_ptr(), weight._version, tuple(weight.shape))
+    cached = getattr(weight, '_c2m_pack', None)
+    if cached is not None and cached[0] == tag:
+        return cached[1]
+    cout, cin = weight.shape[:2]
+    n = _lib.lib().c2m_conv3x3_packed_weight_bytes(cin, cout)
+    blob = torch.empty(n, dtype=torch.uint8, device=weight.device)
+    with torch.cuda.device(weight.device):
+        rc = _lib.lib().c2m_conv3x3_pack_weights_f32(weight.detach().contiguous().data_ptr(), cin, cout,
+                                                     blob.data_ptr(), _stream())
+        _lib.check(rc, 'c2m_conv3x3_pack_weights_f32')
+    try:
+        weight._c2m_pack = (tag, blob)
+    except Exception:
+        pass
     return blob
 
 
