@@ -19,20 +19,32 @@ class DcnShape(ctypes.Structure):
                 ('xs_b', 'xs_c', 'xs_y', 'xs_x', 'os_b', 'os_c', 'os_y', 'os_x')]
 
 
+class ConvArgs(ctypes.Structure):
+    """c2m_conv3x3_args (include/c2m_sm100.h)."""
+    _fields_ = [('in_hi', ctypes.c_void_p), ('in_lo', ctypes.c_void_p), ('Cin', ctypes.c_int),
+                ('in2_hi', ctypes.c_void_p), ('in2_lo', ctypes.c_void_p), ('Cin2', ctypes.c_int),
+                ('B', ctypes.c_int), ('H', ctypes.c_int), ('W', ctypes.c_int), ('sa_in', ctypes.c_int),
+                ('packed_w', ctypes.c_void_p), ('bias', ctypes.c_void_p), ('Cout', ctypes.c_int), ('act', ctypes.c_int),
+                ('res_hi', ctypes.c_void_p), ('res_lo', ctypes.c_void_p), ('res2_hi', ctypes.c_void_p),
+                ('res2_lo', ctypes.c_void_p), ('sa_res', ctypes.c_int),
+                ('out_hi', ctypes.c_void_p), ('out_lo', ctypes.c_void_p), ('sa_out', ctypes.c_int),
+                ('pixel_shuffle', ctypes.c_int),
+                ('out_f32', ctypes.c_void_p), ('add_f32', ctypes.c_void_p),
+                ('os_b', ctypes.c_longlong), ('os_c', ctypes.c_longlong), ('os_y', ctypes.c_longlong),
+                ('os_x', ctypes.c_longlong)]
+
+
 SYMBOLS = {
     'c2m_abi_version': (ctypes.c_int, []),
     'c2m_last_error': (ctypes.c_char_p, []),
     'c2m_launch_count': (ctypes.c_ulonglong, []),
     'c2m_conv3x3_packed_weight_bytes': (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
-    'c2m_conv3x3_supported': (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
     'c2m_conv3x3_pack_weights_f32': (ctypes.c_int, [c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     'c2m_psa_from_f32': (ctypes.c_int, [c_f32p] + [ctypes.c_int] * 4 + [ctypes.c_longlong] * 4 +
                          [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     'c2m_psa_to_f32': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 5 + [c_f32p, c_f32p] +
                        [ctypes.c_longlong] * 4 + [ctypes.c_void_p]),
-    'c2m_conv3x3_psa': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 5 +
-                        [ctypes.c_void_p, c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
-                         ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    'c2m_conv3x3': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     'c2m_profile_enable': (ctypes.c_int, [ctypes.c_int]),
     'c2m_profile_corr_search_ms': (ctypes.c_int, [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)]),
     'c2m_corr_workspace_bytes': (ctypes.c_size_t, [ctypes.c_int] * 9),

@@ -235,10 +235,8 @@ def psa_to_f32(p, add=None, channels_last=False):
 
 
 def conv3x3_supported(cin, cout, H=None, W=None):
-    ok = bool(_lib.lib().c2m_conv3x3_supported(cin, cout))
-    if H is not None:
-        ok = ok and H >= 18 and W >= 10
-    return ok
+    """The tcgen05 kernel takes any channel counts; maps must hold one halo tile (18 x 10)."""
+    return H is None or (H >= 18 and W >= 10)
 
 
 def conv3x3_pack_weights(weight):
@@ -267,20 +265,58 @@ def conv3x3_pack_weights(weight):
 _ACT = {None: 0, 'none': 0, 'relu': 1, 'lrelu': 2}
 
 
-def conv3x3_psa(x, weight, bias, act=None, residual=None, out=None, sa_out=0):
-    """out = act(conv3x3(x, weight) + bias) + residual, all PSA (fp32-grade, tensor cores)."""
+def conv3x3_psa(x, weight, bias, act=None, residual=None, residual2=None, x2=None, out=None, sa_out=0,
+                pixel_shuffle=0, out_f32=False, add_f32=None, psa_out=True, channels_last=False):
+    """y = act(conv3x3(cat[x, x2], weight) + bias), fp32-grade on tensor cores.
+
+    Returns the PSA tensor `y + residual + residual2` (or PixelShuffle(2)(y)), and/or — with
+    out_f32=True — the fp32 tensor `y + add_f32`.  With both, returns (psa, f32)."""
     cout, cin = weight.shape[:2]
-    if cin != x.C:
-        raise RuntimeError(f'conv3x3_psa: weight expects {cin} input channels, got {x.C}')
+    c_in = x.C + (x2.C if x2 is not None else 0)
+    if cin != c_in:
+        raise RuntimeError(f'conv3x3_psa: weight expects {cin} input channels, got {c_in}')
     blob = conv3x3_pack_weights(weight)
-    if out is None:
-        out = PSA.empty(x.B, cout, x.H, x.W, x.hi.device, sa_out)
-    with torch.cuda.device(x.hi.device):
-        rc = _lib.lib().c2m_conv3x3_psa(
-            x.hi.data_ptr(), x.lo.data_ptr(), x.B, cin, x.H, x.W, x.sa, blob.data_ptr(),
-            bias.data_ptr() if bias is not None else None, cout, _ACT[act],
-            residual.hi.data_ptr() if residual is not None else None,
-            residual.lo.data_ptr() if residual is not None else None, residual.sa if residual is not None else 0,
-            out.hi.data_ptr(), out.lo.data_ptr(), out.sa, _stream())
-        _lib.check(rc, 'c2m_conv3x3_psa')
-    return out
+    dev = x.hi.device
+    a = _lib.ConvArgs()
+    a.in_hi, a.in_lo, a.Cin = x.hi.data_ptr(), x.lo.data_ptr(), x.C
+    if x2 is not None:
+        if (x2.B, x2.H, x2.W) != (x.B, x.H, x.W) or x2.sa != x.sa:
+            raise RuntimeError('conv3x3_psa: concatenated inputs must share batch / size / scale')
+        a.in2_hi, a.in2_lo, a.Cin2 = x2.hi.data_ptr(), x2.lo.data_ptr(), x2.C
+    a.B, a.H, a.W, a.sa_in = x.B, x.H, x.W, x.sa
+    a.packed_w, a.bias = blob.data_ptr(), (bias.data_ptr() if bias is not None else None)
+    a.Cout, a.act = cout, _ACT[act]
+    for r, (fh, fl) in ((residual, ('res_hi', 'res_lo')), (residual2, ('res2_hi', 'res2_lo'))):
+        if r is not None:
+            if r.shape != (x.B, cout, x.H, x.W):
+                raise RuntimeError(f'conv3x3_psa: residual shape {r.shape}')
+            setattr(a, fh, r.hi.data_ptr())
+            setattr(a, fl, r.lo.data_ptr())
+            a.sa_res = r.sa
+    a.pixel_shuffle = pixel_shuffle
+    ret_psa = None
+    if psa_out:
+        if out is None:
+            if pixel_shuffle == 2:
+                out = PSA.empty(x.B, cout // 4, 2 * x.H, 2 * x.W, dev, sa_out)
+            else:
+                out = PSA.empty(x.B, cout, x.H, x.W, dev, sa_out)
+        a.out_hi, a.out_lo, a.sa_out = out.hi.data_ptr(), out.lo.data_ptr(), out.sa
+        ret_psa = out
+    ret_f32 = None
+    if out_f32:
+        mf = torch.channels_last if channels_last else torch.contiguous_format
+        ret_f32 = torch.empty(x.B, cout, x.H, x.W, dtype=torch.float32, device=dev, memory_format=mf)
+        a.out_f32 = ret_f32.data_ptr()
+        a.os_b, a.os_c, a.os_y, a.os_x = ret_f32.stride()
+        if add_f32 is not None:
+            if add_f32.shape != ret_f32.shape or add_f32.stride() != ret_f32.stride():
+                add_f32 = add_f32.contiguous(memory_format=mf)
+            a.add_f32 = add_f32.data_ptr()
+    import ctypes
+    with torch.cuda.device(dev):
+        rc = _lib.lib().c2m_conv3x3(ctypes.addressof(a), _stream())
+        _lib.check(rc, 'c2m_conv3x3')
+    if ret_psa is not None and ret_f32 is not None:
+        return ret_psa, ret_f32
+    return ret_psa if ret_psa is not None else ret_f32

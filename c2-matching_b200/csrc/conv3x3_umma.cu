@@ -26,94 +26,133 @@ namespace c2m {
 namespace {
 constexpr int T_R = 16, T_C = 8;          // output pixel tile -> UMMA M = 128
 constexpr int A_R = T_R + 2, A_C = T_C + 2;
-constexpr int KOCT = 4;                   // channel octets per A stage
+constexpr int KOCT = 4;                   // channel octets per K chunk (32 channels)
 constexpr int ROW_B = A_C * 16;           // 160 B  (SBO of A)
 constexpr int A_OCT_B = A_R * ROW_B;      // 2880 B (LBO of A)
 constexpr int A_HALF = KOCT * A_OCT_B;    // 11520 B (hi or lo of one stage)
 constexpr int A_STAGE = 2 * A_HALF;       // 23040 B
-constexpr int NSTAGE = 3;
-constexpr int NACC = 4;
+constexpr int NSTAGE = 3;                 // activation ring
+constexpr int NBST = 2;                   // weight-chunk double buffer
+constexpr int MAXT = 8;                   // pixel tiles per work item (one TMEM accumulator each)
+constexpr int NMAX = 64;                  // output channels per CTA slice
 constexpr int W_HDR = 256;                // packed-weight blob header bytes
 
 struct ConvParams {
-    int B, C8in, H, W;        // input (C8in = channel octets present in the activation tensor)
-    int Cout, N;              // real / padded (multiple of 16) output channels
-    int nkc;                  // K chunks of KOCT octets (weights are padded to nkc*KOCT octets)
-    int tiles_x, tiles_y;
+    int B, H, W;
+    int nkc_a, nkc;           // K chunks taken from input 1 / in total (input 2 supplies the rest)
+    int Cout, N, nslice;      // real couts, couts per CTA slice (multiple of 16, <= 64), slices
+    int tiles_x, tiles_y, T, n_st;   // tile grid, tiles per item, super-tiles per image
     int act;                  // 0 none, 1 relu, 2 leaky relu 0.1
-    int sa_in, sa_res, sa_out;    // activation scale exponents (values are stored * 2^sa)
-    int C8out;
+    int sa_in, sa_res, sa_out;
+    int ps;                   // 0 or 2: PixelShuffle(2) applied to the PSA output
+    int C8out, Hout, Wout;    // geometry of the PSA output tensor
+    long long os_b, os_c, os_y, os_x;   // fp32 output element strides
+};
+struct ConvPtrs {
+    const uint8_t *wblob;
+    const float *bias;
+    const __half *res_hi, *res_lo, *res2_hi, *res2_lo;
+    __half *out_hi, *out_lo;
+    float *out_f32;
+    const float *add_f32;
 };
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
+// Work item = (image, super-tile of up to 8 consecutive 16x8 pixel tiles, 64-wide Cout slice).
+// K loop: for each 32-channel chunk kc the slice's weight chunk (9 taps, hi+lo, N*1152 B) is
+// bulk-copied ONCE into a double-buffered smem slot and used by all T pixel tiles of the item
+// (T TMEM accumulators of N columns), so weight traffic per MMA is 1/T of a per-tile stream and
+// any Cin/Cout fits; 64->64 degenerates to 2 chunks per item.  Activation stages stream
+// through a 3-deep TMA ring exactly as in the correlation kernel.
+// ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 1)
 conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
-                    const uint8_t *__restrict__ wblob, const float *__restrict__ bias,
-                    const __half *__restrict__ res_hi, const __half *__restrict__ res_lo,
-                    __half *__restrict__ out_hi, __half *__restrict__ out_lo, const ConvParams p) {
+                    const __grid_constant__ CUtensorMap tm2_hi, const __grid_constant__ CUtensorMap tm2_lo,
+                    const ConvPtrs q, const ConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const uint32_t w_half = (uint32_t)p.nkc * 9 * KOCT * p.N * 16;      // bytes of W_hi (== W_lo)
-    uint8_t *sW = smem;                                                  // [hi | lo]
-    uint8_t *sA = smem + 2 * w_half;
-    sA = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(sA) + 127) & ~uintptr_t(127));
+    const uint32_t w_half = 9u * KOCT * p.N * 16;                        // bytes of one chunk half
+    const uint32_t w_chunk = 2 * w_half;
+    uint8_t *sW = smem;                                                  // [NBST][hi | lo]
+    uint8_t *sA = smem + NBST * w_chunk;                                 // multiple of 128 already
     uint64_t *bars = reinterpret_cast<uint64_t *>(sA + NSTAGE * A_STAGE);
-    uint64_t *full = bars, *empty = bars + NSTAGE, *tfull = bars + 2 * NSTAGE, *tempty = tfull + NACC,
-             *wbar = tempty + NACC;
-    uint32_t *tmem_base_p = reinterpret_cast<uint32_t *>(wbar + 1);
+    uint64_t *full = bars, *empty = full + NSTAGE, *bfull = empty + NSTAGE, *bempty = bfull + NBST,
+             *tfull = bempty + NBST, *tempty = tfull + MAXT;
+    uint32_t *tmem_base_p = reinterpret_cast<uint32_t *>(tempty + MAXT);
     float *sbias = reinterpret_cast<float *>(tmem_base_p + 2);           // [N]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_tiles = p.B * p.tiles_x * p.tiles_y;
-    const uint32_t tmem_cols = p.N * NACC <= 32 ? 32 : p.N * NACC <= 64 ? 64 : p.N * NACC <= 128 ? 128
-                               : p.N * NACC <= 256 ? 256 : 512;
+    const int tiles_img = p.tiles_x * p.tiles_y;
+    const int n_items = p.B * p.n_st * p.nslice;
+    const uint32_t need_cols = (uint32_t)p.N * p.T;
+    const uint32_t tmem_cols = need_cols <= 32 ? 32 : need_cols <= 64 ? 64 : need_cols <= 128 ? 128
+                               : need_cols <= 256 ? 256 : 512;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_hi);
         tma_prefetch_desc(&tm_lo);
+        tma_prefetch_desc(&tm2_hi);
+        tma_prefetch_desc(&tm2_lo);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < NSTAGE; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < NACC; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
-        mbar_init(wbar, 1);
+        for (int i = 0; i < NBST; ++i) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], 1); }
+        for (int i = 0; i < MAXT; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
         fence_mbar_init();
     }
     if (warp == 2) {
         tmem_alloc(tmem_base_p, tmem_cols);
         tmem_relinquish();
     }
-    for (int i = threadIdx.x; i < p.N; i += blockDim.x) sbias[i] = (bias && i < p.Cout) ? bias[i] : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_p;
-    const int sw = *reinterpret_cast<const int *>(wblob);                // weight scale exponent
+    const int sw = *reinterpret_cast<const int *>(q.wblob);              // weight scale exponent
+
+    // item -> (b, st, slice): slice fastest so concurrently running CTAs share activation tiles in L2
+    auto decode = [&](int item, int &b, int &t0, int &nt, int &slice) {
+        slice = item % p.nslice;
+        const int r = item / p.nslice;
+        const int st = r % p.n_st;
+        b = r / p.n_st;
+        t0 = st * p.T;
+        nt = min(p.T, tiles_img - t0);
+    };
 
     if (warp == 0) {
         // ================================ producer ==========================================
         if (lane == 0) {
-            // weights: one bulk copy per half, once per CTA
-            mbar_arrive_expect_tx(wbar, 2 * w_half);
-            const uint8_t *src = wblob + W_HDR;
-            for (uint32_t off = 0; off < 2 * w_half; off += 65536) {
-                const uint32_t n = min(65536u, 2 * w_half - off);
-                asm volatile(
-                    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                    ::"r"(smem_u32(sW + off)), "l"(src + off), "r"(n), "r"(smem_u32(wbar))
-                    : "memory");
-            }
-            int stage = 0, phase = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int b = tile / (p.tiles_x * p.tiles_y), tt = tile % (p.tiles_x * p.tiles_y);
-                const int y0 = (tt / p.tiles_x) * T_R, x0 = (tt % p.tiles_x) * T_C;
+            int stage = 0, phase = 0, bst = 0, bphase = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                int b, t0, nt, slice;
+                decode(item, b, t0, nt, slice);
                 for (int kc = 0; kc < p.nkc; ++kc) {
-                    mbar_wait(&empty[stage], phase ^ 1);
-                    uint8_t *s = sA + stage * A_STAGE;
-                    mbar_arrive_expect_tx(&full[stage], A_STAGE);
-                    tma_load_4d(s, &tm_hi, &full[stage], (x0 - 1) * 8, y0 - 1, kc * KOCT, b);
-                    tma_load_4d(s + A_HALF, &tm_lo, &full[stage], (x0 - 1) * 8, y0 - 1, kc * KOCT, b);
-                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                    mbar_wait(&bempty[bst], bphase ^ 1);
+                    mbar_arrive_expect_tx(&bfull[bst], w_chunk);
+                    const uint8_t *src = q.wblob + W_HDR + ((size_t)slice * p.nkc + kc) * w_chunk;
+                    for (uint32_t off = 0; off < w_chunk; off += 36864) {
+                        const uint32_t n = min(36864u, w_chunk - off);
+                        asm volatile(
+                            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                            ::"r"(smem_u32(sW + bst * w_chunk + off)), "l"(src + off), "r"(n), "r"(smem_u32(&bfull[bst]))
+                            : "memory");
+                    }
+                    if (++bst == NBST) { bst = 0; bphase ^= 1; }
+                    const bool first = kc < p.nkc_a;
+                    const CUtensorMap *mh = first ? &tm_hi : &tm2_hi, *ml = first ? &tm_lo : &tm2_lo;
+                    const int oct0 = (first ? kc : kc - p.nkc_a) * KOCT;
+                    for (int t = 0; t < nt; ++t) {
+                        const int tt = t0 + t;
+                        const int y0 = (tt / p.tiles_x) * T_R, x0 = (tt % p.tiles_x) * T_C;
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        uint8_t *s = sA + stage * A_STAGE;
+                        mbar_arrive_expect_tx(&full[stage], A_STAGE);
+                        tma_load_4d(s, mh, &full[stage], (x0 - 1) * 8, y0 - 1, oct0, b);
+                        tma_load_4d(s + A_HALF, ml, &full[stage], (x0 - 1) * 8, y0 - 1, oct0, b);
+                        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                    }
                 }
             }
         }
@@ -121,40 +160,48 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
         // ================================ MMA issuer ========================================
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_f16(128, p.N, 0);
-            const uint32_t w_hi = smem_u32(sW), w_lo = w_hi + w_half;
             const uint32_t b_lbo = p.N * 16;                 // next channel octet of the weights
-            mbar_wait(wbar, 0);
-            tc_fence_after();
-            int stage = 0, phase = 0, acc = 0, acc_phase = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                mbar_wait(&tempty[acc], acc_phase ^ 1);
-                tc_fence_after();
-                const uint32_t d = tmem_base + acc * p.N;
+            int stage = 0, phase = 0, bst = 0, bphase = 0;
+            uint32_t tph = 0;                                  // per-accumulator phase bits
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                int b, t0, nt, slice;
+                decode(item, b, t0, nt, slice);
                 for (int kc = 0; kc < p.nkc; ++kc) {
-                    mbar_wait(&full[stage], phase);
+                    mbar_wait(&bfull[bst], bphase);
                     tc_fence_after();
-                    const uint32_t a_hi = smem_u32(sA + stage * A_STAGE), a_lo = a_hi + A_HALF;
-#pragma unroll
-                    for (int tap = 0; tap < 9; ++tap) {
-                        const uint32_t toff = ((tap / 3) * A_C + tap % 3) * 16;
-                        const uint32_t wtap = ((kc * 9 + tap) * KOCT) * b_lbo;
-#pragma unroll
-                        for (int j = 0; j < KOCT / 2; ++j) {
-                            const uint32_t ao = toff + j * 2 * A_OCT_B, bo = wtap + j * 2 * b_lbo;
-                            const uint64_t dah = umma_smem_desc(a_hi + ao, A_OCT_B, ROW_B);
-                            const uint64_t dal = umma_smem_desc(a_lo + ao, A_OCT_B, ROW_B);
-                            const uint64_t dbh = umma_smem_desc(w_hi + bo, b_lbo, 128);
-                            const uint64_t dbl = umma_smem_desc(w_lo + bo, b_lbo, 128);
-                            umma_f16(d, dah, dbh, idesc, (kc | tap | j) != 0);
-                            umma_f16(d, dah, dbl, idesc, 1);
-                            umma_f16(d, dal, dbh, idesc, 1);
+                    const uint32_t w_hi = smem_u32(sW + bst * w_chunk), w_lo = w_hi + w_half;
+                    for (int t = 0; t < nt; ++t) {
+                        if (kc == 0) {
+                            mbar_wait(&tempty[t], ((tph >> t) & 1u) ^ 1u);
+                            tc_fence_after();
                         }
+                        const uint32_t d = tmem_base + t * p.N;
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t a_hi = smem_u32(sA + stage * A_STAGE), a_lo = a_hi + A_HALF;
+#pragma unroll
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const uint32_t toff = ((tap / 3) * A_C + tap % 3) * 16;
+                            const uint32_t wtap = (tap * KOCT) * b_lbo;
+#pragma unroll
+                            for (int j = 0; j < KOCT / 2; ++j) {
+                                const uint32_t ao = toff + j * 2 * A_OCT_B, bo = wtap + j * 2 * b_lbo;
+                                const uint64_t dah = umma_smem_desc(a_hi + ao, A_OCT_B, ROW_B);
+                                const uint64_t dal = umma_smem_desc(a_lo + ao, A_OCT_B, ROW_B);
+                                const uint64_t dbh = umma_smem_desc(w_hi + bo, b_lbo, 128);
+                                const uint64_t dbl = umma_smem_desc(w_lo + bo, b_lbo, 128);
+                                umma_f16(d, dah, dbh, idesc, (kc | tap | j) != 0);
+                                umma_f16(d, dah, dbl, idesc, 1);
+                                umma_f16(d, dal, dbh, idesc, 1);
+                            }
+                        }
+                        umma_commit(&empty[stage]);
+                        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                        if (kc == p.nkc - 1) { umma_commit(&tfull[t]); tph ^= 1u << t; }
                     }
-                    umma_commit(&empty[stage]);
-                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                    umma_commit(&bempty[bst]);
+                    if (++bst == NBST) { bst = 0; bphase ^= 1; }
                 }
-                umma_commit(&tfull[acc]);
-                if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else if (warp >= 4) {
@@ -164,69 +211,122 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
         const float out_scale = ldexpf(1.f, -(p.sa_in + sw));
         const float res_scale = ldexpf(1.f, -p.sa_res);
         const float so = ldexpf(1.f, p.sa_out);
-        int acc = 0, acc_phase = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int b = tile / (p.tiles_x * p.tiles_y), tt = tile % (p.tiles_x * p.tiles_y);
-            const int y = (tt / p.tiles_x) * T_R + e / T_C, x = (tt % p.tiles_x) * T_C + e % T_C;
-            const bool ok = y < p.H && x < p.W;
-            mbar_wait(&tfull[acc], acc_phase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * p.N;
-            for (int c0 = 0; c0 < p.N; c0 += 32) {
-                uint32_t reg[32];
-                if (p.N - c0 >= 32) {
-                    tmem_ld_32x32(taddr + c0, reg);
-                } else {   // N = 16 tail: 16 columns
-                    asm volatile(
-                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                        : "=r"(reg[0]), "=r"(reg[1]), "=r"(reg[2]), "=r"(reg[3]), "=r"(reg[4]), "=r"(reg[5]),
-                          "=r"(reg[6]), "=r"(reg[7]), "=r"(reg[8]), "=r"(reg[9]), "=r"(reg[10]), "=r"(reg[11]),
-                          "=r"(reg[12]), "=r"(reg[13]), "=r"(reg[14]), "=r"(reg[15])
-                        : "r"(taddr + c0)
-                        : "memory");
-                }
-                tmem_ld_wait();
-                if (ok) {
+        uint32_t tph = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            int b, t0, nt, slice;
+            decode(item, b, t0, nt, slice);
+            const int o_base = slice * NMAX;
+            asm volatile("bar.sync 1, 128;" ::: "memory");          // previous item's sbias readers are done
+            if (e < p.N) sbias[e] = (q.bias && o_base + e < p.Cout) ? q.bias[o_base + e] : 0.f;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int t = 0; t < nt; ++t) {
+                const int tt = t0 + t;
+                const int y = (tt / p.tiles_x) * T_R + e / T_C, x = (tt % p.tiles_x) * T_C + e % T_C;
+                const bool ok = y < p.H && x < p.W;
+                mbar_wait(&tfull[t], (tph >> t) & 1u);
+                tph ^= 1u << t;
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + t * p.N;
+                for (int c0 = 0; c0 < p.N; c0 += 32) {
+                    uint32_t reg[32];
+                    if (p.N - c0 >= 32) {
+                        tmem_ld_32x32(taddr + c0, reg);
+                    } else {   // 16-column tail
+                        asm volatile(
+                            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                            : "=r"(reg[0]), "=r"(reg[1]), "=r"(reg[2]), "=r"(reg[3]), "=r"(reg[4]), "=r"(reg[5]),
+                              "=r"(reg[6]), "=r"(reg[7]), "=r"(reg[8]), "=r"(reg[9]), "=r"(reg[10]), "=r"(reg[11]),
+                              "=r"(reg[12]), "=r"(reg[13]), "=r"(reg[14]), "=r"(reg[15])
+                            : "r"(taddr + c0)
+                            : "memory");
+                    }
+                    tmem_ld_wait();
+                    if (!ok) continue;
                     const int ncol = min(32, p.N - c0);
+                    float v[32];
 #pragma unroll
-                    for (int o8 = 0; o8 < 4; ++o8) {
-                        const int oct = c0 / 8 + o8;
-                        if (o8 * 8 >= ncol || oct >= p.C8out) break;
-                        const size_t off = ((((size_t)b * p.C8out + oct) * p.H + y) * p.W + x) * 8;
-                        float r8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                        if (res_hi) {
-                            const uint4 rh = *reinterpret_cast<const uint4 *>(res_hi + off);
-                            const uint4 rl = *reinterpret_cast<const uint4 *>(res_lo + off);
-                            const __half *hh = reinterpret_cast<const __half *>(&rh);
-                            const __half *ll = reinterpret_cast<const __half *>(&rl);
+                    for (int j = 0; j < 32; ++j) {
+                        float a = fmaf(__uint_as_float(reg[j]), out_scale, sbias[(c0 + j) & (NMAX - 1)]);
+                        if (p.act == 1) a = fmaxf(a, 0.f);
+                        else if (p.act == 2) a = a > 0.f ? a : a * 0.1f;
+                        v[j] = (j < ncol && o_base + c0 + j < p.Cout) ? a : 0.f;
+                    }
+                    if (q.out_f32) {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) r8[j] = (__half2float(hh[j]) + __half2float(ll[j])) * res_scale;
+                        for (int j = 0; j < 32; ++j) {
+                            const int o = o_base + c0 + j;
+                            if (j < ncol && o < p.Cout) {
+                                const long long oi = b * p.os_b + o * p.os_c + y * p.os_y + x * p.os_x;
+                                q.out_f32[oi] = q.add_f32 ? v[j] + q.add_f32[oi] : v[j];
+                            }
                         }
-                        __align__(16) __half h8[8];
-                        __align__(16) __half l8[8];
+                    }
+                    if (q.out_hi && p.ps == 0) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int o = c0 + o8 * 8 + j;
-                            float v = fmaf(__uint_as_float(reg[o8 * 8 + j]), out_scale, sbias[o]);
-                            if (p.act == 1) v = fmaxf(v, 0.f);
-                            else if (p.act == 2) v = v > 0.f ? v : v * 0.1f;
-                            v += r8[j];
-                            if (o >= p.Cout) v = 0.f;
-                            const float vs = v * so;
-                            const __half hh = __float2half_rn(vs);
-                            h8[j] = hh;
-                            l8[j] = __float2half_rn(vs - __half2float(hh));
+                        for (int o8 = 0; o8 < 4; ++o8) {
+                            const int oct = (o_base + c0) / 8 + o8;
+                            if (o8 * 8 >= ncol || oct >= p.C8out) break;
+                            const size_t off = ((((size_t)b * p.C8out + oct) * p.H + y) * p.W + x) * 8;
+                            float r8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                            if (q.res_hi) {
+                                const uint4 rh = *reinterpret_cast<const uint4 *>(q.res_hi + off);
+                                const uint4 rl = *reinterpret_cast<const uint4 *>(q.res_lo + off);
+                                const __half *hh = reinterpret_cast<const __half *>(&rh);
+                                const __half *ll = reinterpret_cast<const __half *>(&rl);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) r8[j] = (__half2float(hh[j]) + __half2float(ll[j])) * res_scale;
+                            }
+                            if (q.res2_hi) {
+                                const uint4 rh = *reinterpret_cast<const uint4 *>(q.res2_hi + off);
+                                const uint4 rl = *reinterpret_cast<const uint4 *>(q.res2_lo + off);
+                                const __half *hh = reinterpret_cast<const __half *>(&rh);
+                                const __half *ll = reinterpret_cast<const __half *>(&rl);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) r8[j] += (__half2float(hh[j]) + __half2float(ll[j])) * res_scale;
+                            }
+                            __align__(16) __half h8[8];
+                            __align__(16) __half l8[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const int o = o_base + c0 + o8 * 8 + j;
+                                const float vs = (o < p.Cout ? v[o8 * 8 + j] + r8[j] : 0.f) * so;
+                                const __half hh = __float2half_rn(vs);
+                                h8[j] = hh;
+                                l8[j] = __float2half_rn(vs - __half2float(hh));
+                            }
+                            *reinterpret_cast<uint4 *>(q.out_hi + off) = *reinterpret_cast<const uint4 *>(h8);
+                            *reinterpret_cast<uint4 *>(q.out_lo + off) = *reinterpret_cast<const uint4 *>(l8);
                         }
-                        *reinterpret_cast<uint4 *>(out_hi + off) = *reinterpret_cast<const uint4 *>(h8);
-                        *reinterpret_cast<uint4 *>(out_lo + off) = *reinterpret_cast<const uint4 *>(l8);
+                    }
+                    if (q.out_hi && p.ps == 2) {
+                        // PixelShuffle(2): conv channel o = 4c + 2i + j  ->  out[c][2y+i][2x+j]
+                        // the 32 columns at c0 hold c = (o_base+c0)/4 .. +7  = exactly one output octet
+                        const int oct = (o_base + c0) / 32;
+                        if (oct < p.C8out && ncol == 32) {
+#pragma unroll
+                            for (int ij = 0; ij < 4; ++ij) {
+                                const size_t off = ((((size_t)b * p.C8out + oct) * p.Hout + 2 * y + (ij >> 1)) * p.Wout +
+                                                    2 * x + (ij & 1)) * 8;
+                                __align__(16) __half h8[8];
+                                __align__(16) __half l8[8];
+#pragma unroll
+                                for (int c = 0; c < 8; ++c) {
+                                    const float vs = v[c * 4 + ij] * so;
+                                    const __half hh = __float2half_rn(vs);
+                                    h8[c] = hh;
+                                    l8[c] = __float2half_rn(vs - __half2float(hh));
+                                }
+                                *reinterpret_cast<uint4 *>(q.out_hi + off) = *reinterpret_cast<const uint4 *>(h8);
+                                *reinterpret_cast<uint4 *>(q.out_lo + off) = *reinterpret_cast<const uint4 *>(l8);
+                            }
+                        }
                     }
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[t]);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
-            if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
         }
     }
 
@@ -306,8 +406,9 @@ __global__ void wamax_kernel(const float *__restrict__ w, int n, unsigned *__res
     if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(bits, __float_as_uint(m));
 }
 
-// blob: [int sw][unsigned amax_bits]...pad to 256 B | W_hi [nkc][9][KOCT][N][8] | W_lo (same)
-__global__ void wpack_kernel(const float *__restrict__ w, int Cin, int Cout, int N, int nkc, uint8_t *__restrict__ blob) {
+// blob: [int sw][unsigned amax_bits]...pad to 256 B | [slice][kc][hi|lo][tap][octet][N][8] fp16
+__global__ void wpack_kernel(const float *__restrict__ w, int Cin, int Cout, int N, int nkc, int nslice,
+                             uint8_t *__restrict__ blob) {
     __shared__ int s_sw;
     if (threadIdx.x == 0) {
         const float a = __uint_as_float(reinterpret_cast<unsigned *>(blob)[1]);
@@ -318,18 +419,22 @@ __global__ void wpack_kernel(const float *__restrict__ w, int Cin, int Cout, int
     }
     __syncthreads();
     const float S = ldexpf(1.f, s_sw);
-    const int half_elems = nkc * 9 * KOCT * N * 8;
-    __half *hi = reinterpret_cast<__half *>(blob + W_HDR);
-    __half *lo = hi + half_elems;
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < half_elems; e += gridDim.x * blockDim.x) {
-        const int j = e & 7, o = (e >> 3) % N, rest = (e >> 3) / N;
-        const int oct = rest % KOCT, tap = (rest / KOCT) % 9, kc = rest / (KOCT * 9);
-        const int c = (kc * KOCT + oct) * 8 + j;
+    const long long total = (long long)nslice * nkc * 2 * 9 * KOCT * N * 8;
+    __half *dst = reinterpret_cast<__half *>(blob + W_HDR);
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(e & 7);
+        long long rest = e >> 3;
+        const int ol = (int)(rest % N); rest /= N;
+        const int oct = (int)(rest % KOCT); rest /= KOCT;
+        const int tap = (int)(rest % 9); rest /= 9;
+        const int half = (int)(rest % 2); rest /= 2;
+        const int kc = (int)(rest % nkc);
+        const int slice = (int)(rest / nkc);
+        const int c = (kc * KOCT + oct) * 8 + j, o = slice * NMAX + ol;
         float v = 0.f;
         if (c < Cin && o < Cout) v = w[((size_t)o * Cin + c) * 9 + tap] * S;
         const __half hh = __float2half_rn(v);
-        hi[e] = hh;
-        lo[e] = __float2half_rn(v - __half2float(hh));
+        dst[e] = half ? __float2half_rn(v - __half2float(hh)) : hh;
     }
 }
 
@@ -363,6 +468,8 @@ static int make_act_map(CUtensorMap *m, const void *base, int B, int C8, int H, 
 
 static inline int pad16(int c) { return (c + 15) / 16 * 16; }
 static inline int n_kc(int cin) { return ((cin + 7) / 8 + KOCT - 1) / KOCT; }
+static inline int slice_n(int cout) { return cout <= NMAX ? pad16(cout) : NMAX; }
+static inline int n_slice(int cout) { return cout <= NMAX ? 1 : (cout + NMAX - 1) / NMAX; }
 
 }  // namespace c2m
 
@@ -370,13 +477,7 @@ using namespace c2m;
 
 extern "C" size_t c2m_conv3x3_packed_weight_bytes(int Cin, int Cout) {
     if (Cin <= 0 || Cout <= 0) return 0;
-    return (size_t)W_HDR + 2 * (size_t)n_kc(Cin) * 9 * KOCT * pad16(Cout) * 16;
-}
-
-extern "C" int c2m_conv3x3_supported(int Cin, int Cout) {
-    if (Cin <= 0 || Cout <= 0 || pad16(Cout) > 128) return 0;
-    const size_t smem = 2 * (size_t)n_kc(Cin) * 9 * KOCT * pad16(Cout) * 16 + NSTAGE * A_STAGE + 4096;
-    return smem <= 227 * 1024 ? 1 : 0;
+    return (size_t)W_HDR + (size_t)n_slice(Cout) * n_kc(Cin) * 2 * 9 * KOCT * slice_n(Cout) * 16;
 }
 
 extern "C" int c2m_conv3x3_pack_weights_f32(const float *w, int Cin, int Cout, void *packed, c2m_stream_t stream) {
@@ -387,10 +488,10 @@ extern "C" int c2m_conv3x3_pack_weights_f32(const float *w, int Cin, int Cout, v
     wamax_kernel<<<ceil_div(n, 1024) > 64 ? 64 : ceil_div(n, 1024), 256, 0, st>>>(
         w, n, reinterpret_cast<unsigned *>(packed) + 1);
     C2M_LAUNCH_CHECK("wamax_kernel");
-    const int N = pad16(Cout), nkc = n_kc(Cin);
-    const int total = nkc * 9 * KOCT * N * 8;
-    wpack_kernel<<<ceil_div(total, 256) > 296 ? 296 : ceil_div(total, 256), 256, 0, st>>>(
-        w, Cin, Cout, N, nkc, reinterpret_cast<uint8_t *>(packed));
+    const int N = slice_n(Cout), nkc = n_kc(Cin), ns = n_slice(Cout);
+    const long long total = (long long)ns * nkc * 2 * 9 * KOCT * N * 8;
+    const int blocks = (int)((total + 255) / 256 > 592 ? 592 : (total + 255) / 256);
+    wpack_kernel<<<blocks, 256, 0, st>>>(w, Cin, Cout, N, nkc, ns, reinterpret_cast<uint8_t *>(packed));
     C2M_LAUNCH_CHECK("wpack_kernel");
     return C2M_OK;
 }
@@ -423,36 +524,63 @@ extern "C" int c2m_psa_to_f32(const void *hi, const void *lo, int B, int C, int 
     return C2M_OK;
 }
 
-extern "C" int c2m_conv3x3_psa(const void *in_hi, const void *in_lo, int B, int Cin, int H, int W, int sa_in,
-                               const void *packed_w, const float *bias, int Cout, int act, const void *res_hi,
-                               const void *res_lo, int sa_res, void *out_hi, void *out_lo, int sa_out,
-                               c2m_stream_t stream) {
-    C2M_CHECK_ARG(in_hi && in_lo && packed_w && out_hi && out_lo, "conv3x3_psa: null pointer");
-    C2M_CHECK_ARG(B > 0 && Cin > 0 && Cout > 0 && H > 0 && W > 0, "conv3x3_psa: bad shape");
-    C2M_CHECK_ARG(c2m_conv3x3_supported(Cin, Cout), "conv3x3_psa: %d -> %d channels exceed the resident-weight kernel",
-                  Cin, Cout);
-    C2M_CHECK_ARG((res_hi == nullptr) == (res_lo == nullptr), "conv3x3_psa: residual needs both halves");
-    C2M_CHECK_ARG(act >= 0 && act <= 2, "conv3x3_psa: unknown activation %d", act);
+extern "C" int c2m_conv3x3(const c2m_conv3x3_args *a, c2m_stream_t stream) {
+    C2M_CHECK_ARG(a, "conv3x3: null args");
+    C2M_CHECK_ARG(a->in_hi && a->in_lo && a->packed_w, "conv3x3: null input / weights");
+    C2M_CHECK_ARG(a->B > 0 && a->Cin > 0 && a->Cout > 0, "conv3x3: bad shape");
+    C2M_CHECK_ARG(a->H >= A_R && a->W >= A_C, "conv3x3: map %dx%d smaller than one halo tile (18x10)", a->H, a->W);
+    C2M_CHECK_ARG((a->in2_hi == nullptr) == (a->Cin2 == 0) && (a->in2_hi == nullptr) == (a->in2_lo == nullptr),
+                  "conv3x3: inconsistent second input");
+    C2M_CHECK_ARG(a->Cin2 == 0 || a->Cin % (KOCT * 8) == 0,
+                  "conv3x3: first of two concatenated inputs must have a multiple of 32 channels (got %d)", a->Cin);
+    C2M_CHECK_ARG((a->res_hi == nullptr) == (a->res_lo == nullptr) && (a->res2_hi == nullptr) == (a->res2_lo == nullptr),
+                  "conv3x3: residual needs both halves");
+    C2M_CHECK_ARG(a->act >= 0 && a->act <= 2, "conv3x3: unknown activation %d", a->act);
+    C2M_CHECK_ARG((a->out_hi == nullptr) == (a->out_lo == nullptr), "conv3x3: PSA output needs both halves");
+    C2M_CHECK_ARG(a->out_hi || a->out_f32, "conv3x3: no output requested");
+    C2M_CHECK_ARG(a->pixel_shuffle == 0 || (a->pixel_shuffle == 2 && a->Cout % 32 == 0 && a->out_hi && !a->res_hi),
+                  "conv3x3: pixel_shuffle must be 0 or 2 (Cout %% 32 == 0, PSA output, no residual)");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     ConvParams p;
-    p.B = B; p.C8in = (Cin + 7) / 8; p.H = H; p.W = W;
-    p.Cout = Cout; p.N = pad16(Cout); p.nkc = n_kc(Cin);
-    p.tiles_x = ceil_div(W, T_C); p.tiles_y = ceil_div(H, T_R);
-    p.act = act; p.sa_in = sa_in; p.sa_res = sa_res; p.sa_out = sa_out;
-    p.C8out = (Cout + 7) / 8;
-    CUtensorMap mh, ml;
+    p.B = a->B; p.H = a->H; p.W = a->W;
+    p.nkc_a = n_kc(a->Cin);
+    p.nkc = a->Cin2 ? a->Cin / (KOCT * 8) + n_kc(a->Cin2) : p.nkc_a;
+    if (a->Cin2) p.nkc_a = a->Cin / (KOCT * 8);
+    p.Cout = a->Cout; p.N = slice_n(a->Cout); p.nslice = n_slice(a->Cout);
+    p.tiles_x = ceil_div(a->W, T_C); p.tiles_y = ceil_div(a->H, T_R);
+    p.T = MAXT;
+    p.n_st = ceil_div(p.tiles_x * p.tiles_y, p.T);
+    p.act = a->act; p.sa_in = a->sa_in; p.sa_res = a->sa_res; p.sa_out = a->sa_out;
+    p.ps = a->pixel_shuffle;
+    const int c_out_psa = p.ps == 2 ? a->Cout / 4 : a->Cout;
+    p.C8out = (c_out_psa + 7) / 8;
+    p.Hout = p.ps == 2 ? 2 * a->H : a->H;
+    p.Wout = p.ps == 2 ? 2 * a->W : a->W;
+    p.os_b = a->os_b; p.os_c = a->os_c; p.os_y = a->os_y; p.os_x = a->os_x;
+    ConvPtrs q;
+    q.wblob = reinterpret_cast<const uint8_t *>(a->packed_w);
+    q.bias = a->bias;
+    q.res_hi = reinterpret_cast<const __half *>(a->res_hi); q.res_lo = reinterpret_cast<const __half *>(a->res_lo);
+    q.res2_hi = reinterpret_cast<const __half *>(a->res2_hi); q.res2_lo = reinterpret_cast<const __half *>(a->res2_lo);
+    q.out_hi = reinterpret_cast<__half *>(a->out_hi); q.out_lo = reinterpret_cast<__half *>(a->out_lo);
+    q.out_f32 = a->out_f32; q.add_f32 = a->add_f32;
+    CUtensorMap mh, ml, m2h, m2l;
     int rc;
-    if ((rc = make_act_map(&mh, in_hi, B, p.C8in, H, W))) return rc;
-    if ((rc = make_act_map(&ml, in_lo, B, p.C8in, H, W))) return rc;
-    const size_t smem = 2 * (size_t)p.nkc * 9 * KOCT * p.N * 16 + NSTAGE * A_STAGE + 4096 + 1024;
+    if ((rc = make_act_map(&mh, a->in_hi, a->B, (a->Cin + 7) / 8, a->H, a->W))) return rc;
+    if ((rc = make_act_map(&ml, a->in_lo, a->B, (a->Cin + 7) / 8, a->H, a->W))) return rc;
+    if (a->Cin2) {
+        if ((rc = make_act_map(&m2h, a->in2_hi, a->B, (a->Cin2 + 7) / 8, a->H, a->W))) return rc;
+        if ((rc = make_act_map(&m2l, a->in2_lo, a->B, (a->Cin2 + 7) / 8, a->H, a->W))) return rc;
+    } else {
+        m2h = mh; m2l = ml;
+    }
+    const size_t smem = (size_t)NBST * 2 * 9 * KOCT * p.N * 16 + NSTAGE * A_STAGE + 1024 + 1024;
     C2M_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 0;
     C2M_CUDA(cudaGetDevice(&dev));
     C2M_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int n_tiles = B * p.tiles_x * p.tiles_y;
-    conv3x3_umma_kernel<<<n_tiles < sms ? n_tiles : sms, 256, smem, st>>>(
-        mh, ml, reinterpret_cast<const uint8_t *>(packed_w), bias, reinterpret_cast<const __half *>(res_hi),
-        reinterpret_cast<const __half *>(res_lo), reinterpret_cast<__half *>(out_hi), reinterpret_cast<__half *>(out_lo), p);
+    const int n_items = a->B * p.n_st * p.nslice;
+    conv3x3_umma_kernel<<<n_items < sms ? n_items : sms, 256, smem, st>>>(mh, ml, m2h, m2l, q, p);
     C2M_LAUNCH_CHECK("conv3x3_umma_kernel");
     return C2M_OK;
 }

@@ -116,15 +116,19 @@ class DCN_sep_pre_multi_offset(_WithOffsetConv):
         feat = x
         if self.extra_offset_mask:
             x, feat = x[0], x[1]
+        return self.fused_tail(x, self.conv_offset_mask(feat), pre_offset, lrelu_slope, channels_last_out)
+
+    def fused_tail(self, x, om, pre_offset, lrelu_slope=1.0, channels_last_out=False):
+        """Everything after the conv_offset_mask convolution (dcn_v2.py:230-253), one kernel.
+        `om`: raw conv_offset_mask output [B, 3*dg*9, H, W] fp32."""
         if self.stride != (1, 1) or self.dilation != (1, 1):
             raise NotImplementedError('fused pre-offset DCN supports stride 1 / dilation 1 (all C2-Matching uses)')
-        om = self.conv_offset_mask(feat)
         if self.debug_offset_check:
             mean = om[:, :om.shape[1] // 3 * 2].abs().mean()
             if mean > 100:
                 logger.warning(f'Offset mean is {mean}, larger than 100.')
         idx = getattr(pre_offset, 'max_idx', None)
-        if idx is not None:      # PreOffsets handle from CorrespondenceGenerationArch: no pyramid in HBM
+        if idx is not None:      # ScaleOffsets handle from CorrespondenceGenerationArch: no pyramid in HBM
             return _ops.dcn_v2_fused_forward(x, om, self.weight, self.bias, self.deformable_groups, idx=idx,
                                              pre_scale=pre_offset.scale, ref_gw=pre_offset.ref_gw,
                                              lrelu_slope=lrelu_slope, channels_last_out=channels_last_out)

@@ -52,42 +52,68 @@ def fast_conv_enabled():
     return os.environ.get('C2M_FAST_CONV', '1') != '0'
 
 
-def psa_conv_ok(conv, H, W):
-    """True if `conv` (3x3, stride 1, pad 1) can run on the tcgen05 kernel for an HxW map."""
+def psa_path_ok(x, *convs):
+    """True if the tcgen05 3x3 kernel can take over for tensor `x` [B,C,H,W] and these convs."""
+    if not (fast_conv_enabled() and x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled()):
+        return False
+    if x.shape[2] < 18 or x.shape[3] < 10:
+        return False
+    return all(isinstance(c, nn.Conv2d) and c.kernel_size == (3, 3) and c.stride == (1, 1) and c.padding == (1, 1) and
+               c.dilation == (1, 1) and c.groups == 1 and c.weight.is_cuda for c in convs)
+
+
+def conv_psa(conv, xp, act=None, **kw):
+    """One nn.Conv2d (3x3/s1/p1) on a packed-split activation."""
     from c2m_b200 import ops
-    return (fast_conv_enabled() and isinstance(conv, nn.Conv2d) and conv.kernel_size == (3, 3) and
-            conv.stride == (1, 1) and conv.padding == (1, 1) and conv.dilation == (1, 1) and conv.groups == 1 and
-            conv.weight.is_cuda and not torch.is_grad_enabled() and
-            ops.conv3x3_supported(conv.in_channels, conv.out_channels, H, W))
+    return ops.conv3x3_psa(xp, conv.weight, conv.bias, act=act, **kw)
 
 
-def resblocks_psa(body, hp):
+def resblocks_psa(body, hp, final_residual2=None):
     """Run a Sequential of ResidualBlockNoBN on a packed-split activation (PSA) with the tcgen05
     3x3 kernel: x + conv2(relu(conv1(x))) per block, two launches per block, no fp32 round trip.
-    Three PSA buffers are cycled."""
+    `final_residual2` is added in the last block's epilogue (the `body(h) + x` skip of
+    ref_restoration_arch.py:158,171,184).  Three PSA buffers are cycled."""
     from c2m_b200 import ops
     bufs = [hp, ops.PSA.empty(hp.B, hp.C, hp.H, hp.W, hp.hi.device), ops.PSA.empty(hp.B, hp.C, hp.H, hp.W, hp.hi.device)]
     cur = 0
-    for blk in body:
-        t, nxt = bufs[(cur + 1) % 3], bufs[(cur + 2) % 3]
-        ops.conv3x3_psa(bufs[cur], blk.conv1.weight, blk.conv1.bias, act='relu', out=t)
-        res = bufs[cur]
+    n = len(body)
+    for i, blk in enumerate(body):
         if blk.res_scale != 1:
             raise NotImplementedError('res_scale != 1 is not used by C2-Matching')
-        ops.conv3x3_psa(t, blk.conv2.weight, blk.conv2.bias, act=None, residual=res, out=nxt)
+        t, nxt = bufs[(cur + 1) % 3], bufs[(cur + 2) % 3]
+        ops.conv3x3_psa(bufs[cur], blk.conv1.weight, blk.conv1.bias, act='relu', out=t)
+        ops.conv3x3_psa(t, blk.conv2.weight, blk.conv2.bias, act=None, residual=bufs[cur],
+                        residual2=final_residual2 if i == n - 1 else None, out=nxt)
         cur = (cur + 2) % 3
     return bufs[cur]
 
 
 def body_forward(body, h, skip=None):
-    """body(h) (+ skip): tcgen05 path when supported, else the plain modules."""
+    """body(h) (+ skip) on fp32 tensors: tcgen05 path when supported, else the plain modules."""
     from c2m_b200 import ops
-    blk0 = body[0]
-    if h.is_cuda and all(isinstance(b, ResidualBlockNoBN) for b in body) and psa_conv_ok(blk0.conv1, h.shape[2], h.shape[3]):
+    if all(isinstance(b, ResidualBlockNoBN) for b in body) and psa_path_ok(h, body[0].conv1, body[0].conv2):
         out = resblocks_psa(body, ops.psa_from_f32(h))
         return ops.psa_to_f32(out, add=skip)
     y = body(h)
     return y if skip is None else y + skip
+
+
+def attach_psa(t, psa):
+    """Remember the packed-split twin of an fp32 feature tensor (consumed by the next fast conv)."""
+    try:
+        t._c2m_psa = psa
+    except Exception:
+        pass
+    return t
+
+
+def psa_of(t):
+    """Packed-split version of fp32 tensor `t` (reusing the twin a producer attached, if any)."""
+    from c2m_b200 import ops
+    p = getattr(t, '_c2m_psa', None)
+    if p is not None and p.shape == tuple(t.shape):
+        return p
+    return ops.psa_from_f32(t)
 
 
 def make_layer(block, n_blocks, **kwargs):

@@ -5,7 +5,7 @@ reference's `feature_extraction.pth` loads strictly."""
 import torch
 from torch import nn
 
-from .vgg_arch import build_trunk
+from .vgg_arch import build_trunk, run_trunk
 
 
 class ContrasExtractorLayer(nn.Module):
@@ -17,7 +17,7 @@ class ContrasExtractorLayer(nn.Module):
         self.register_buffer('std', torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1))
 
     def forward(self, batch):
-        return self.model((batch - self.mean) / self.std)
+        return run_trunk(self.model, (batch - self.mean) / self.std)[0]
 
 
 class ContrasExtractorSep(nn.Module):

@@ -25,12 +25,15 @@ class ContentExtractor(nn.Module):
         self.body = arch_util.make_layer(arch_util.ResidualBlockNoBN, n_blocks, nf=nf)
         arch_util.default_init_weights([self.conv_first], 0.1)
 
+    def forward_psa(self, x):
+        from c2m_b200 import ops
+        hp = arch_util.conv_psa(self.conv_first, ops.psa_from_f32(x), act='lrelu')
+        return arch_util.resblocks_psa(self.body, hp)
+
     def forward(self, x):
         from c2m_b200 import ops
-        if x.is_cuda and arch_util.psa_conv_ok(self.conv_first, x.shape[2], x.shape[3]) and \
-                arch_util.psa_conv_ok(self.body[0].conv1, x.shape[2], x.shape[3]):
-            hp = ops.conv3x3_psa(ops.psa_from_f32(x), self.conv_first.weight, self.conv_first.bias, act='lrelu')
-            return ops.psa_to_f32(arch_util.resblocks_psa(self.body, hp))
+        if arch_util.psa_path_ok(x, self.conv_first, self.body[0].conv1):
+            return ops.psa_to_f32(self.forward_psa(x))
         return self.body(F.leaky_relu(self.conv_first(x), 0.1))
 
 
@@ -50,27 +53,46 @@ class DynamicAggregationRestoration(nn.Module):
         self.tail_large = nn.Sequential(nn.Conv2d(ngf, ngf // 2, 3, 1, 1), nn.LeakyReLU(0.1, True),
                                         nn.Conv2d(ngf // 2, 3, 3, 1, 1))
 
+    @staticmethod
+    def _pre(pre_offset, key):
+        return pre_offset.handle(key) if hasattr(pre_offset, 'handle') else pre_offset[key]
+
     def forward(self, x, pre_offset, img_ref_feat):
+        """Module path: plain convolutions through cuDNN (used for tiny maps / C2M_FAST_CONV=0)."""
         for size, key, _ in _LEVELS:
             ref = img_ref_feat[key]
             off = torch.cat([x, ref], 1)
             off = F.leaky_relu_(getattr(self, f'{size}_offset_conv1')(off), 0.1)
             off = F.leaky_relu_(getattr(self, f'{size}_offset_conv2')(off), 0.1)
-            pre = pre_offset.handle(key) if hasattr(pre_offset, 'handle') else pre_offset[key]
-            swapped = getattr(self, f'{size}_dyn_agg')([ref, off], pre, lrelu_slope=0.1)   # lrelu fused
+            swapped = getattr(self, f'{size}_dyn_agg')([ref, off], self._pre(pre_offset, key), lrelu_slope=0.1)
             h = getattr(self, f'head_{size}')(torch.cat([x, swapped], 1))
             h = arch_util.body_forward(getattr(self, f'body_{size}'), h, skip=x)
-            x = self._tail(size, h)
+            x = getattr(self, f'tail_{size}')(h)
         return x
 
-    def _tail(self, size, h):
-        tail = getattr(self, f'tail_{size}')
-        if size == 'large' and h.is_cuda and arch_util.psa_conv_ok(tail[0], h.shape[2], h.shape[3]) and \
-                arch_util.psa_conv_ok(tail[2], h.shape[2], h.shape[3]):
-            from c2m_b200 import ops
-            t = ops.conv3x3_psa(ops.psa_from_f32(h), tail[0].weight, tail[0].bias, act='lrelu')
-            return ops.psa_to_f32(ops.conv3x3_psa(t, tail[2].weight, tail[2].bias))
-        return tail(h)
+    def forward_psa(self, xp, pre_offset, img_ref_feat, base):
+        """tcgen05 path: every plain convolution runs in the packed-split layout; `cat` is a
+        two-input convolution, PixelShuffle and the final `+ base` are conv epilogues; only the
+        DCN boundary (fp32 offsets/mask in, fp32 features out) leaves the layout."""
+        from c2m_b200 import ops
+        out = None
+        for size, key, _ in _LEVELS:
+            ref = img_ref_feat[key]
+            refp = arch_util.psa_of(ref)
+            dyn = getattr(self, f'{size}_dyn_agg')
+            off = arch_util.conv_psa(getattr(self, f'{size}_offset_conv1'), xp, act='lrelu', x2=refp)
+            off = arch_util.conv_psa(getattr(self, f'{size}_offset_conv2'), off, act='lrelu')
+            om = arch_util.conv_psa(dyn.conv_offset_mask, off, psa_out=False, out_f32=True)
+            swapped = dyn.fused_tail(ref, om, self._pre(pre_offset, key), lrelu_slope=0.1)
+            h = arch_util.conv_psa(getattr(self, f'head_{size}')[0], xp, act='lrelu', x2=ops.psa_from_f32(swapped))
+            h = arch_util.resblocks_psa(getattr(self, f'body_{size}'), h, final_residual2=xp)
+            tail = getattr(self, f'tail_{size}')
+            if size != 'large':
+                xp = arch_util.conv_psa(tail[0], h, act='lrelu', pixel_shuffle=2)
+            else:
+                t = arch_util.conv_psa(tail[0], h, act='lrelu')
+                out = arch_util.conv_psa(tail[2], t, psa_out=False, out_f32=True, add_f32=base)
+        return out
 
 
 class RestorationNet(nn.Module):
@@ -88,5 +110,8 @@ class RestorationNet(nn.Module):
 
     def forward(self, x, pre_offset, img_ref_feat):
         base = F.interpolate(x, None, 4, 'bilinear', False)
-        content_feat = self.content_extractor(x)
-        return self.dyn_agg_restore(content_feat, pre_offset, img_ref_feat) + base
+        ce, dr = self.content_extractor, self.dyn_agg_restore
+        if arch_util.psa_path_ok(x, ce.conv_first, dr.small_offset_conv1, dr.head_small[0], dr.tail_large[2]):
+            return dr.forward_psa(ce.forward_psa(x), pre_offset, img_ref_feat, base.contiguous())
+        content_feat = ce(x)
+        return dr(content_feat, pre_offset, img_ref_feat) + base

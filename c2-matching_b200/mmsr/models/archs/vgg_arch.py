@@ -64,6 +64,61 @@ def load_imagenet(trunk, vgg_type, path=None):
         m.bias.data.copy_(tv[f'features.{n}.bias'])
 
 
+def run_trunk(trunk, x, taps=(), want_last_f32=True):
+    """Run a named VGG trunk (Sequential of conv / relu / pool).  Returns (last, {tap: fp32}).
+
+    tcgen05 path: each conv+ReLU pair is one launch in the packed-split layout; a tapped ReLU
+    output is written both as fp32 (for the DCN sampler / the caller) and packed (attached to the
+    fp32 tensor for the next consumer); convs before a max-pool emit fp32 for torch's pooling."""
+    from . import arch_util
+    from c2m_b200 import ops
+    layers = list(trunk.named_children())
+    convs = [m for _, m in layers if isinstance(m, nn.Conv2d)]
+    if not arch_util.psa_path_ok(x, *convs) or x.shape[2] < 72 or x.shape[3] < 40:
+        got = {}
+        for name, layer in layers:
+            if isinstance(layer, nn.ReLU):
+                x = torch.relu(x)
+            else:
+                x = layer(x)
+            if name in taps:
+                got[name] = x
+        return x, got
+    got = {}
+    xp, xf = ops.psa_from_f32(x), None
+    i = 0
+    while i < len(layers):
+        name, layer = layers[i]
+        if isinstance(layer, nn.Conv2d):
+            has_relu = i + 1 < len(layers) and isinstance(layers[i + 1][1], nn.ReLU)
+            out_name = layers[i + 1][0] if has_relu else name
+            nxt = layers[i + 2][1] if has_relu and i + 2 < len(layers) else (layers[i + 1][1] if not has_relu and i + 1 < len(layers) else None)
+            last = nxt is None
+            need_f32 = out_name in taps or isinstance(nxt, nn.MaxPool2d) or (last and want_last_f32)
+            need_psa = isinstance(nxt, nn.Conv2d) or out_name in taps
+            if xp is None:
+                xp = ops.psa_from_f32(xf)
+            r = ops.conv3x3_psa(xp, layer.weight, layer.bias, act='relu' if has_relu else None, psa_out=need_psa,
+                                out_f32=need_f32)
+            if need_psa and need_f32:
+                xp, xf = r
+                arch_util.attach_psa(xf, xp)
+            elif need_psa:
+                xp, xf = r, None
+            else:
+                xp, xf = None, r
+            if out_name in taps:
+                got[out_name] = xf
+            i += 2 if has_relu else 1
+        elif isinstance(layer, nn.MaxPool2d):
+            xf = layer(xf)
+            xp = None
+            i += 1
+        else:
+            raise RuntimeError(f'unexpected layer {name} in VGG trunk')
+    return (xf if xf is not None else ops.psa_to_f32(xp)), got
+
+
 class VGGFeatureExtractor(nn.Module):
     """Returns {layer_name: feature} for the requested layers — vgg_arch.py:59-145."""
 
@@ -89,13 +144,5 @@ class VGGFeatureExtractor(nn.Module):
     def forward(self, x):
         if self.use_input_norm:
             x = (x - self.mean) / self.std
-        out = {}
-        for name, layer in self.vgg_net.named_children():
-            if isinstance(layer, nn.ReLU) and name in self.layer_name_list:
-                x = torch.relu(x)          # out-of-place: the tapped tensor must survive
-                out[name] = x
-                continue
-            x = layer(x)
-            if name in self.layer_name_list:
-                out[name] = x.clone() if not isinstance(layer, nn.ReLU) else x
-        return out
+        _, got = run_trunk(self.vgg_net, x, taps=self.layer_name_list, want_last_f32=False)
+        return got

@@ -109,27 +109,37 @@ int c2m_dcn_v2_fused_forward_f32(const float *x, const float *om, const float *p
                                  const c2m_dcn_shape *shape, c2m_stream_t stream);
 
 /* --- plain 3x3 / stride 1 / pad 1 convolution on tcgen05, fp32-grade (split fp16 x 3) -------
- * (the ResidualBlockNoBN chains of RestorationNet, arch_util.py:80-136.)
+ * (every plain convolution of RestorationNet / the VGG trunks; the reference
+ * runs them through cuDNN, e.g. arch_util.py:80-136, ref_restoration_arch.py:147-187.)
  * Activations travel between these convolutions in the packed-split layout "PSA":
  *     hi, lo : fp16 [B][ceil(C/8)][H][W][8],   value = (hi + lo) * 2^-sa
  * c2m_psa_from_f32 / c2m_psa_to_f32 convert from / to strided fp32 ([B,C,H,W] with element
- * strides; to_f32 can add a strided fp32 tensor of the same strides, e.g. a skip connection).
+ * strides; to_f32 can add a strided fp32 tensor of the same strides).
  * Weights [Cout,Cin,3,3] fp32 are packed once (c2m_conv3x3_pack_weights_f32) into a blob of
- * c2m_conv3x3_packed_weight_bytes(Cin,Cout) bytes.  c2m_conv3x3_supported: 1 if the
- * resident-weight kernel covers the channel counts (e.g. 64->64, 64->32, 32->3, 3->64).
- *     out = act(conv(in, W) + bias) + res        act: 0 none, 1 ReLU, 2 LeakyReLU(0.1)
- * res (optional) and out are PSA tensors with Cout channels.  Needs H >= 18 and W >= 10.
+ * c2m_conv3x3_packed_weight_bytes(Cin,Cout) bytes (Cin = total input channels).
+ *     y = act(conv(cat[in, in2], W) + bias)          act: 0 none, 1 ReLU, 2 LeakyReLU(0.1)
+ *     PSA output  (optional): y + res + res2, or PixelShuffle(2)(y) when pixel_shuffle == 2
+ *     fp32 output (optional): y + add_f32, strided [B,Cout,H,W]
+ * Any Cin / Cout; in2 (optional) is concatenated after in along channels (then Cin % 32 == 0).
+ * Needs H >= 18 and W >= 10.
  */
+typedef struct {
+    const void *in_hi, *in_lo;   int Cin;
+    const void *in2_hi, *in2_lo; int Cin2;
+    int B, H, W, sa_in;
+    const void *packed_w; const float *bias; int Cout; int act;
+    const void *res_hi, *res_lo, *res2_hi, *res2_lo; int sa_res;
+    void *out_hi, *out_lo; int sa_out; int pixel_shuffle;
+    float *out_f32; const float *add_f32; long long os_b, os_c, os_y, os_x;
+} c2m_conv3x3_args;
+
 size_t c2m_conv3x3_packed_weight_bytes(int Cin, int Cout);
-int c2m_conv3x3_supported(int Cin, int Cout);
 int c2m_conv3x3_pack_weights_f32(const float *w, int Cin, int Cout, void *packed, c2m_stream_t stream);
 int c2m_psa_from_f32(const float *x, int B, int C, int H, int W, long long xs_b, long long xs_c, long long xs_y,
                      long long xs_x, int sa, void *hi, void *lo, c2m_stream_t stream);
 int c2m_psa_to_f32(const void *hi, const void *lo, int B, int C, int H, int W, int sa, const float *add, float *out,
                    long long os_b, long long os_c, long long os_y, long long os_x, c2m_stream_t stream);
-int c2m_conv3x3_psa(const void *in_hi, const void *in_lo, int B, int Cin, int H, int W, int sa_in,
-                    const void *packed_w, const float *bias, int Cout, int act, const void *res_hi,
-                    const void *res_lo, int sa_res, void *out_hi, void *out_lo, int sa_out, c2m_stream_t stream);
+int c2m_conv3x3(const c2m_conv3x3_args *args, c2m_stream_t stream);
 
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 unsigned long long c2m_launch_count(void);

@@ -364,3 +364,55 @@ def test_resblock_chain_fast_path_equals_module_path():
         fast = arch_util.body_forward(body, h, skip=skip)
         slow = body(h) + skip
     _rel_ok(fast, slow, 2e-5)
+
+
+def test_conv3x3_general_modes_vs_fp64():
+    """Generalised tcgen05 conv: two concatenated inputs, >64 output channels (sliced), fused
+    PixelShuffle(2), fp32 strided output with an added tensor, both outputs at once."""
+    from c2m_b200 import ops
+    for (B, c1, c2, cout, H, W, act, mode) in ((1, 64, 256, 256, 40, 40, 'lrelu', 'psa'), (2, 64, 128, 128, 24, 40, 'lrelu', 'psa'),
+                                               (1, 128, 0, 216, 36, 30, None, 'f32'), (1, 64, 0, 256, 32, 24, 'lrelu', 'ps2'),
+                                               (1, 256, 0, 256, 20, 26, 'relu', 'both'), (1, 32, 0, 3, 40, 48, None, 'f32add'),
+                                               (1, 64, 64, 64, 130, 70, 'lrelu', 'psa')):
+        x1 = seeding.randn(11, (B, c1, H, W), 1.2)
+        x2 = seeding.randn(12, (B, c2, H, W), 0.8) if c2 else None
+        w = seeding.randn(13, (cout, c1 + c2, 3, 3), 0.03)
+        b = seeding.randn(14, (cout,), 0.5)
+        want = F.conv2d((torch.cat([x1, x2], 1) if c2 else x1).double(), w.double(), b.double(), 1, 1)
+        want = want.relu() if act == 'relu' else F.leaky_relu(want, 0.1) if act == 'lrelu' else want
+        p1 = ops.psa_from_f32(x1.to(DEV))
+        p2 = ops.psa_from_f32(x2.to(DEV)) if c2 else None
+        wd, bd = w.to(DEV), b.to(DEV)
+        if mode == 'psa':
+            got = ops.psa_to_f32(ops.conv3x3_psa(p1, wd, bd, act=act, x2=p2))
+        elif mode == 'f32':
+            got = ops.conv3x3_psa(p1, wd, bd, act=act, psa_out=False, out_f32=True)
+        elif mode == 'f32add':
+            add = seeding.randn(15, (B, cout, H, W))
+            got = ops.conv3x3_psa(p1, wd, bd, act=act, psa_out=False, out_f32=True, add_f32=add.to(DEV))
+            want = want + add.double()
+        elif mode == 'ps2':
+            got = ops.psa_to_f32(ops.conv3x3_psa(p1, wd, bd, act=act, pixel_shuffle=2))
+            want = F.pixel_shuffle(want, 2)
+        else:
+            gp, got = ops.conv3x3_psa(p1, wd, bd, act=act, out_f32=True)
+            assert float((ops.psa_to_f32(gp) - got).abs().max()) <= 1e-6 * float(want.abs().max())
+        err = float((got.cpu().double() - want).abs().max())
+        assert err <= 3e-5 * float(want.abs().max()), (mode, err)
+
+
+def test_fast_conv_path_equals_cudnn_path(monkeypatch):
+    """The whole pipeline with every plain conv on the tcgen05 kernel vs the same pipeline with
+    them on exact-fp32 cuDNN (C2M_FAST_CONV=0): same index map, SR within 1e-3 relative."""
+    from c2m_b200.pipeline import RestorationPipeline
+    sd_e, sd_m, sd_g = _weights()
+    pipe = RestorationPipeline(DEV).load_state_dicts(sd_e, sd_m, sd_g).place()
+    hr, img_lq, img_up, img_ref = seeding.full_case_inputs('b2')
+    args = [t.to(DEV) for t in (img_lq, img_up, img_ref)]
+    sr_fast, idx_fast = pipe.forward(*args, return_idx=True)
+    monkeypatch.setenv('C2M_FAST_CONV', '0')
+    sr_slow, idx_slow = pipe.forward(*args, return_idx=True)
+    flips = int((idx_fast != idx_slow).sum())
+    assert flips <= 2
+    if flips == 0:
+        _rel_ok(sr_fast, sr_slow, 1e-3)

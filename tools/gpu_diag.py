@@ -169,6 +169,73 @@ def conv_diag():
                   f'[cuDNN fp32 pre-act err {float((cud.double() - F.conv2d(x.double(), w.double(), b.double(), 1, 1)).abs().max()):.3e}]', flush=True)
         except Exception:
             traceback.print_exc()
+    section('conv3x3 general: dual input / slices / pixel shuffle / fp32 out')
+    for (B, c1, c2, cout, H, W, act, mode) in ((1, 64, 256, 256, 40, 40, 'lrelu', 'psa'), (2, 64, 128, 128, 24, 40, 'lrelu', 'psa'),
+                                               (1, 128, 0, 216, 36, 30, None, 'f32'), (1, 64, 0, 256, 32, 24, 'lrelu', 'ps2'),
+                                               (1, 256, 0, 256, 20, 26, 'relu', 'both'), (1, 32, 0, 3, 40, 48, None, 'f32add'),
+                                               (1, 64, 64, 64, 130, 70, 'lrelu', 'psa')):
+        try:
+            x1 = seeding.randn(11, (B, c1, H, W), 1.2)
+            x2 = seeding.randn(12, (B, c2, H, W), 0.8) if c2 else None
+            cin = c1 + c2
+            w = seeding.randn(13, (cout, cin, 3, 3), 0.03)
+            b = seeding.randn(14, (cout,), 0.5)
+            xin = torch.cat([x1, x2], 1) if c2 else x1
+            want = F.conv2d(xin.double(), w.double(), b.double(), 1, 1)
+            want = want.relu() if act == 'relu' else F.leaky_relu(want, 0.1) if act == 'lrelu' else want
+            p1 = ops.psa_from_f32(x1.to(dev))
+            p2 = ops.psa_from_f32(x2.to(dev)) if c2 else None
+            wd, bd = w.to(dev), b.to(dev)
+            if mode == 'psa':
+                got = ops.psa_to_f32(ops.conv3x3_psa(p1, wd, bd, act=act, x2=p2)).cpu()
+            elif mode == 'f32':
+                got = ops.conv3x3_psa(p1, wd, bd, act=act, x2=p2, psa_out=False, out_f32=True).cpu()
+            elif mode == 'f32add':
+                add = seeding.randn(15, (B, cout, H, W))
+                got = ops.conv3x3_psa(p1, wd, bd, act=act, x2=p2, psa_out=False, out_f32=True, add_f32=add.to(dev)).cpu()
+                want = want + add.double()
+            elif mode == 'ps2':
+                got = ops.psa_to_f32(ops.conv3x3_psa(p1, wd, bd, act=act, pixel_shuffle=2)).cpu()
+                want = F.pixel_shuffle(want, 2)
+            else:
+                gp, gf = ops.conv3x3_psa(p1, wd, bd, act=act, out_f32=True)
+                got = gf.cpu()
+                print('   both: psa vs f32 diff', float((ops.psa_to_f32(gp).cpu() - got).abs().max()))
+            torch.cuda.synchronize()
+            print(f'B{B} {c1}+{c2}->{cout} {H}x{W} {mode}: max err {float((got.double() - want).abs().max()):.3e} (scale {float(want.abs().max()):.2f})', flush=True)
+        except Exception:
+            traceback.print_exc()
+    section('conv3x3 timing (B=4)')
+    for (cin, cout, H) in ((128, 64, 640), (64, 216, 640), (192, 128, 320), (320, 256, 160), (256, 256, 160), (64, 256, 320)):
+        try:
+            x = torch.randn(4, cin, H, H, device=dev)
+            w = torch.randn(cout, cin, 3, 3, device=dev) * 0.03
+            b = torch.randn(cout, device=dev)
+            xp = ops.psa_from_f32(x)
+            yp = ops.PSA.empty(4, cout, H, H, dev)
+            for _ in range(3):
+                ops.conv3x3_psa(xp, w, b, act='lrelu', out=yp)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                ops.conv3x3_psa(xp, w, b, act='lrelu', out=yp)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 5
+            torch.backends.cudnn.allow_tf32 = False
+            for _ in range(2):
+                F.conv2d(x, w, b, 1, 1)
+            e0.record()
+            for _ in range(3):
+                F.conv2d(x, w, b, 1, 1)
+            e1.record()
+            torch.cuda.synchronize()
+            ms_c = e0.elapsed_time(e1) / 3
+            fl = 2 * cin * cout * 9 * H * H * 4
+            print(f'{cin}->{cout} @{H}: c2m {ms:.3f} ms ({fl / ms / 1e9:.0f} TFLOP/s alg); cuDNN fp32 {ms_c:.3f} ms', flush=True)
+        except Exception:
+            traceback.print_exc()
     section('conv3x3 timing, 64->64, B=4')
     for H in (160, 320, 640):
         x = torch.randn(4, 64, H, H, device=dev)
