@@ -34,6 +34,20 @@ class ConvArgs(ctypes.Structure):
                 ('os_x', ctypes.c_longlong)]
 
 
+class DcnTcArgs(ctypes.Structure):
+    """c2m_dcn_tc_args (include/c2m_sm100.h)."""
+    _fields_ = [('x', ctypes.c_void_p), ('xs_b', ctypes.c_longlong), ('xs_c', ctypes.c_longlong),
+                ('xs_y', ctypes.c_longlong), ('xs_x', ctypes.c_longlong),
+                ('om', ctypes.c_void_p), ('pre', ctypes.c_void_p), ('idx', ctypes.c_void_p),
+                ('gh', ctypes.c_int), ('gw', ctypes.c_int), ('ref_gw', ctypes.c_int), ('pre_scale', ctypes.c_int),
+                ('B', ctypes.c_int), ('C', ctypes.c_int), ('H', ctypes.c_int), ('W', ctypes.c_int),
+                ('Cout', ctypes.c_int), ('dg', ctypes.c_int),
+                ('packed_w', ctypes.c_void_p), ('bias', ctypes.c_void_p), ('lrelu', ctypes.c_int),
+                ('out_hi', ctypes.c_void_p), ('out_lo', ctypes.c_void_p), ('sa_out', ctypes.c_int),
+                ('out_f32', ctypes.c_void_p), ('os_b', ctypes.c_longlong), ('os_c', ctypes.c_longlong),
+                ('os_y', ctypes.c_longlong), ('os_x', ctypes.c_longlong)]
+
+
 SYMBOLS = {
     'c2m_abi_version': (ctypes.c_int, []),
     'c2m_last_error': (ctypes.c_char_p, []),
@@ -45,6 +59,10 @@ SYMBOLS = {
     'c2m_psa_to_f32': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 5 + [c_f32p, c_f32p] +
                        [ctypes.c_longlong] * 4 + [ctypes.c_void_p]),
     'c2m_conv3x3': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    'c2m_dcn_tc_supported': (ctypes.c_int, [ctypes.c_int] * 3),
+    'c2m_dcn_tc_packed_weight_bytes': (ctypes.c_size_t, [ctypes.c_int] * 3),
+    'c2m_dcn_tc_pack_weights_f32': (ctypes.c_int, [c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    'c2m_dcn_v2_fused_tc': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     'c2m_profile_enable': (ctypes.c_int, [ctypes.c_int]),
     'c2m_profile_corr_search_ms': (ctypes.c_int, [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)]),
     'c2m_corr_workspace_bytes': (ctypes.c_size_t, [ctypes.c_int] * 9),

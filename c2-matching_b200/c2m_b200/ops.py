@@ -320,3 +320,79 @@ def conv3x3_psa(x, weight, bias, act=None, residual=None, residual2=None, x2=Non
     if ret_psa is not None and ret_f32 is not None:
         return ret_psa, ret_f32
     return ret_psa if ret_psa is not None else ret_f32
+
+
+# ------------------------------------------------------------------------------------------------
+# DCNv2 on tensor cores
+def dcn_tc_supported(C, Cout, dg, kh=3, kw=3):
+    return kh == 3 and kw == 3 and bool(_lib.lib().c2m_dcn_tc_supported(C, Cout, dg))
+
+
+def _dcn_tc_pack(weight, dg):
+    tag = (weight.data_ptr(), weight._version, tuple(weight.shape), dg)
+    cached = getattr(weight, '_c2m_dcn_pack', None)
+    if cached is not None and cached[0] == tag:
+        return cached[1]
+    cout, c = weight.shape[:2]
+    n = _lib.lib().c2m_dcn_tc_packed_weight_bytes(c, cout, dg)
+    blob = torch.empty(n, dtype=torch.uint8, device=weight.device)
+    with torch.cuda.device(weight.device):
+        rc = _lib.lib().c2m_dcn_tc_pack_weights_f32(weight.detach().contiguous().data_ptr(), c, cout, dg,
+                                                    blob.data_ptr(), _stream())
+        _lib.check(rc, 'c2m_dcn_tc_pack_weights_f32')
+    try:
+        weight._c2m_dcn_pack = (tag, blob)
+    except Exception:
+        pass
+    return blob
+
+
+def dcn_v2_fused_tc(x, om, weight, bias, deformable_group, pre_offset=None, idx=None, pre_scale=1, ref_gw=None,
+                    lrelu=False, psa_out=False, out_f32=True, channels_last_out=False):
+    """Tensor-core version of dcn_v2_fused_forward (3x3/s1/p1/d1).  Returns fp32 and / or PSA."""
+    import ctypes
+    _require_cuda('x', x)
+    _require_cuda('om', om)
+    B, C, H, W = x.shape
+    cout = weight.shape[0]
+    if not x.is_contiguous(memory_format=torch.channels_last):
+        x = x.contiguous(memory_format=torch.channels_last)
+    om = om.contiguous()
+    if tuple(om.shape) != (B, 27 * deformable_group, H, W):
+        raise RuntimeError(f'conv_offset_mask output has shape {tuple(om.shape)}')
+    a = _lib.DcnTcArgs()
+    a.x = x.data_ptr()
+    a.xs_b, a.xs_c, a.xs_y, a.xs_x = x.stride()
+    a.om = om.data_ptr()
+    if pre_offset is not None:
+        _require_cuda('pre_offset', pre_offset)
+        if tuple(pre_offset.shape) != (B, 9, H, W, 2):
+            raise RuntimeError(f'pre_offset has shape {tuple(pre_offset.shape)}')
+        pre_offset = pre_offset.contiguous()
+        a.pre = pre_offset.data_ptr()
+    elif idx is not None:
+        _require_cuda('idx', idx, torch.int64)
+        idx = idx.contiguous()
+        a.idx = idx.data_ptr()
+        a.gh, a.gw = idx.shape[1:]
+        a.ref_gw, a.pre_scale = (ref_gw or idx.shape[2]), pre_scale
+    a.B, a.C, a.H, a.W, a.Cout, a.dg = B, C, H, W, cout, deformable_group
+    blob = _dcn_tc_pack(weight, deformable_group)
+    a.packed_w = blob.data_ptr()
+    a.bias = bias.contiguous().data_ptr() if bias is not None else None
+    a.lrelu = int(bool(lrelu))
+    ret_p = ret_f = None
+    if psa_out:
+        ret_p = PSA.empty(B, cout, H, W, x.device)
+        a.out_hi, a.out_lo, a.sa_out = ret_p.hi.data_ptr(), ret_p.lo.data_ptr(), 0
+    if out_f32:
+        mf = torch.channels_last if channels_last_out else torch.contiguous_format
+        ret_f = torch.empty(B, cout, H, W, dtype=torch.float32, device=x.device, memory_format=mf)
+        a.out_f32 = ret_f.data_ptr()
+        a.os_b, a.os_c, a.os_y, a.os_x = ret_f.stride()
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().c2m_dcn_v2_fused_tc(ctypes.addressof(a), _stream())
+        _lib.check(rc, 'c2m_dcn_v2_fused_tc')
+    if ret_p is not None and ret_f is not None:
+        return ret_p, ret_f
+    return ret_p if ret_p is not None else ret_f

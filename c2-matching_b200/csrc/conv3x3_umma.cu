@@ -19,7 +19,7 @@
 // on weights.  Epilogue (4 warps, one output pixel per thread): *2^-(sa+sw) + bias, ReLU /
 // LeakyReLU, optional residual add (a second PSA tensor), re-split to hi/lo and store — the
 // output is directly the next convolution's operand, no fp32 round trip through HBM.
-#include "c2m_common.cuh"
+#include "umma_conv_common.cuh"
 
 namespace c2m {
 
@@ -37,25 +37,6 @@ constexpr int MAXT = 8;                   // pixel tiles per work item (one TMEM
 constexpr int NMAX = 64;                  // output channels per CTA slice
 constexpr int W_HDR = 256;                // packed-weight blob header bytes
 
-struct ConvParams {
-    int B, H, W;
-    int nkc_a, nkc;           // K chunks taken from input 1 / in total (input 2 supplies the rest)
-    int Cout, N, nslice;      // real couts, couts per CTA slice (multiple of 16, <= 64), slices
-    int tiles_x, tiles_y, T, n_st;   // tile grid, tiles per item, super-tiles per image
-    int act;                  // 0 none, 1 relu, 2 leaky relu 0.1
-    int sa_in, sa_res, sa_out;
-    int ps;                   // 0 or 2: PixelShuffle(2) applied to the PSA output
-    int C8out, Hout, Wout;    // geometry of the PSA output tensor
-    long long os_b, os_c, os_y, os_x;   // fp32 output element strides
-};
-struct ConvPtrs {
-    const uint8_t *wblob;
-    const float *bias;
-    const __half *res_hi, *res_lo, *res2_hi, *res2_lo;
-    __half *out_hi, *out_lo;
-    float *out_f32;
-    const float *add_f32;
-};
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
@@ -215,7 +196,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             int b, t0, nt, slice;
             decode(item, b, t0, nt, slice);
-            const int o_base = slice * NMAX;
+            const int o_base = slice * p.N;
             asm volatile("bar.sync 1, 128;" ::: "memory");          // previous item's sbias readers are done
             if (e < p.N) sbias[e] = (q.bias && o_base + e < p.Cout) ? q.bias[o_base + e] : 0.f;
             asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -227,102 +208,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                 tph ^= 1u << t;
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + t * p.N;
-                for (int c0 = 0; c0 < p.N; c0 += 32) {
-                    uint32_t reg[32];
-                    if (p.N - c0 >= 32) {
-                        tmem_ld_32x32(taddr + c0, reg);
-                    } else {   // 16-column tail
-                        asm volatile(
-                            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-                            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                            : "=r"(reg[0]), "=r"(reg[1]), "=r"(reg[2]), "=r"(reg[3]), "=r"(reg[4]), "=r"(reg[5]),
-                              "=r"(reg[6]), "=r"(reg[7]), "=r"(reg[8]), "=r"(reg[9]), "=r"(reg[10]), "=r"(reg[11]),
-                              "=r"(reg[12]), "=r"(reg[13]), "=r"(reg[14]), "=r"(reg[15])
-                            : "r"(taddr + c0)
-                            : "memory");
-                    }
-                    tmem_ld_wait();
-                    if (!ok) continue;
-                    const int ncol = min(32, p.N - c0);
-                    float v[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float a = fmaf(__uint_as_float(reg[j]), out_scale, sbias[(c0 + j) & (NMAX - 1)]);
-                        if (p.act == 1) a = fmaxf(a, 0.f);
-                        else if (p.act == 2) a = a > 0.f ? a : a * 0.1f;
-                        v[j] = (j < ncol && o_base + c0 + j < p.Cout) ? a : 0.f;
-                    }
-                    if (q.out_f32) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int o = o_base + c0 + j;
-                            if (j < ncol && o < p.Cout) {
-                                const long long oi = b * p.os_b + o * p.os_c + y * p.os_y + x * p.os_x;
-                                q.out_f32[oi] = q.add_f32 ? v[j] + q.add_f32[oi] : v[j];
-                            }
-                        }
-                    }
-                    if (q.out_hi && p.ps == 0) {
-#pragma unroll
-                        for (int o8 = 0; o8 < 4; ++o8) {
-                            const int oct = (o_base + c0) / 8 + o8;
-                            if (o8 * 8 >= ncol || oct >= p.C8out) break;
-                            const size_t off = ((((size_t)b * p.C8out + oct) * p.H + y) * p.W + x) * 8;
-                            float r8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                            if (q.res_hi) {
-                                const uint4 rh = *reinterpret_cast<const uint4 *>(q.res_hi + off);
-                                const uint4 rl = *reinterpret_cast<const uint4 *>(q.res_lo + off);
-                                const __half *hh = reinterpret_cast<const __half *>(&rh);
-                                const __half *ll = reinterpret_cast<const __half *>(&rl);
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) r8[j] = (__half2float(hh[j]) + __half2float(ll[j])) * res_scale;
-                            }
-                            if (q.res2_hi) {
-                                const uint4 rh = *reinterpret_cast<const uint4 *>(q.res2_hi + off);
-                                const uint4 rl = *reinterpret_cast<const uint4 *>(q.res2_lo + off);
-                                const __half *hh = reinterpret_cast<const __half *>(&rh);
-                                const __half *ll = reinterpret_cast<const __half *>(&rl);
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) r8[j] += (__half2float(hh[j]) + __half2float(ll[j])) * res_scale;
-                            }
-                            __align__(16) __half h8[8];
-                            __align__(16) __half l8[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const int o = o_base + c0 + o8 * 8 + j;
-                                const float vs = (o < p.Cout ? v[o8 * 8 + j] + r8[j] : 0.f) * so;
-                                const __half hh = __float2half_rn(vs);
-                                h8[j] = hh;
-                                l8[j] = __float2half_rn(vs - __half2float(hh));
-                            }
-                            *reinterpret_cast<uint4 *>(q.out_hi + off) = *reinterpret_cast<const uint4 *>(h8);
-                            *reinterpret_cast<uint4 *>(q.out_lo + off) = *reinterpret_cast<const uint4 *>(l8);
-                        }
-                    }
-                    if (q.out_hi && p.ps == 2) {
-                        // PixelShuffle(2): conv channel o = 4c + 2i + j  ->  out[c][2y+i][2x+j]
-                        // the 32 columns at c0 hold c = (o_base+c0)/4 .. +7  = exactly one output octet
-                        const int oct = (o_base + c0) / 32;
-                        if (oct < p.C8out && ncol == 32) {
-#pragma unroll
-                            for (int ij = 0; ij < 4; ++ij) {
-                                const size_t off = ((((size_t)b * p.C8out + oct) * p.Hout + 2 * y + (ij >> 1)) * p.Wout +
-                                                    2 * x + (ij & 1)) * 8;
-                                __align__(16) __half h8[8];
-                                __align__(16) __half l8[8];
-#pragma unroll
-                                for (int c = 0; c < 8; ++c) {
-                                    const float vs = v[c * 4 + ij] * so;
-                                    const __half hh = __float2half_rn(vs);
-                                    h8[c] = hh;
-                                    l8[c] = __float2half_rn(vs - __half2float(hh));
-                                }
-                                *reinterpret_cast<uint4 *>(q.out_hi + off) = *reinterpret_cast<const uint4 *>(h8);
-                                *reinterpret_cast<uint4 *>(q.out_lo + off) = *reinterpret_cast<const uint4 *>(l8);
-                            }
-                        }
-                    }
-                }
+                epilogue_store_tile(q, p, taddr, b, y, x, ok, o_base, sbias, out_scale, res_scale, so);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[t]);
@@ -574,7 +460,7 @@ extern "C" int c2m_conv3x3(const c2m_conv3x3_args *a, c2m_stream_t stream) {
     } else {
         m2h = mh; m2l = ml;
     }
-    const size_t smem = (size_t)NBST * 2 * 9 * KOCT * p.N * 16 + NSTAGE * A_STAGE + 1024 + 1024;
+    const size_t smem = (size_t)NBST * 2 * 9 * KOCT * p.N * 16 + NSTAGE * A_STAGE + 4096;
     C2M_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 0;
     C2M_CUDA(cudaGetDevice(&dev));

@@ -1,0 +1,434 @@
+// Modulated deformable convolution v2 forward on the sm_100a tensor cores (3x3, stride 1, pad 1,
+// dilation 1 — every DCN of C2-Matching), fused with DCN_sep_pre_multi_offset's prologue.
+//
+// Replaces `_ext.dcn_v2_forward` (mmsr/models/archs/DCNv2/src/cuda/dcn_v2_cuda.cu:42-172: im2col
+// into a 236-944 MB `columns` buffer + batched fp32 SGEMM) and the Python prologue
+// (DCNv2/dcn_v2.py:233-250).  Sampling arithmetic follows dcn_v2_im2col_cuda.cu:25-54,125-195
+// operation for operation; the contraction is a split-fp16 (hi*hi + hi*lo + lo*hi) tcgen05 GEMM
+// with fp32 TMEM accumulation, i.e. fp32-grade.
+//
+// Structure = conv3x3_umma.cu with the TMA activation producer replaced by GATHER warps:
+//   K is ordered (deformable group g, tap, channel-in-group); a K chunk = 4 channel octets.
+//   8 gather warps build, per (pixel tile, chunk), the column tile [4 octets][128 px][8] directly in
+//   the tcgen05 K-major no-swizzle layout (hi and lo halves): per (pixel, g, tap) the sampling point
+//   is computed once (raw conv_offset_mask output + pre-offset rebuilt from the index map or read
+//   from the pre_offset tensor, sigmoid mask, validity of the 4 corners), the 8 channels of an octet
+//   are fetched as 2 x 16 B per corner from the channels-last fp32 input, blended in fp32,
+//   multiplied by the mask, split and stored with one 16 B st.shared per half;
+//   fence.proxy.async + mbarrier hand the stage to the MMA-issuing thread.
+//   Weights stream as 8 KB chunks (bulk copy, 4-deep ring), shared by the item's 8 pixel tiles
+//   (8 TMEM accumulators); the epilogue (bias, LeakyReLU, PSA and / or fp32 store) is shared with
+//   the plain convolution.
+// The im2col matrix never exists outside shared memory.
+#include "umma_conv_common.cuh"
+
+namespace c2m {
+
+namespace {
+constexpr int T_R = 16, T_C = 8;
+constexpr int KOCT = 4;
+constexpr int A_OCT_B = 128 * 16;          // 2048 B: one octet of all 128 pixels (LBO of A)
+constexpr int A_HALF = KOCT * A_OCT_B;     // 8192 B
+constexpr int A_STAGE = 2 * A_HALF;        // 16384 B
+constexpr int NSTAGE = 4;
+constexpr int NBST = 4;
+constexpr int MAXT = 8;
+constexpr int NGATHER_WARPS = 8;
+constexpr int W_HDR = 256;
+
+struct DcnTc {
+    const float *x;            // channels-last addressing via element strides
+    long long xs_b, xs_c, xs_y, xs_x;
+    const float *om;           // [B, 3*dg*9, H, W]
+    const float *pre;          // [B, 9, H, W, 2] or null
+    const long long *idx;      // [B, gh, gw] or null
+    int gh, gw, ref_gw, pre_scale;
+    int C, dg, cpg, opp;       // opp = octets per (g, tap) pair = cpg / 8
+    int n_ko;                  // real K octets = C/8 * 9
+};
+}  // namespace
+
+__global__ void __launch_bounds__(512, 1)
+dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t w_half = (uint32_t)KOCT * p.N * 16;
+    const uint32_t w_chunk = 2 * w_half;
+    uint8_t *sW = smem;                                   // [NBST][hi | lo]
+    uint8_t *sA = smem + NBST * w_chunk;                  // N multiple of 16 -> multiple of 128
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sA + NSTAGE * A_STAGE);
+    uint64_t *full = bars, *empty = full + NSTAGE, *bfull = empty + NSTAGE, *bempty = bfull + NBST,
+             *tfull = bempty + NBST, *tempty = tfull + MAXT;
+    uint32_t *tmem_base_p = reinterpret_cast<uint32_t *>(tempty + MAXT);
+    float *sbias = reinterpret_cast<float *>(tmem_base_p + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_img = p.tiles_x * p.tiles_y;
+    const int n_items = p.B * p.n_st * p.nslice;
+    const uint32_t need_cols = (uint32_t)p.N * p.T;
+    const uint32_t tmem_cols = need_cols <= 32 ? 32 : need_cols <= 64 ? 64 : need_cols <= 128 ? 128
+                               : need_cols <= 256 ? 256 : 512;
+
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < NSTAGE; ++i) { mbar_init(&full[i], NGATHER_WARPS); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < NBST; ++i) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], 1); }
+        for (int i = 0; i < MAXT; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_base_p, tmem_cols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_p;
+    const int sw = *reinterpret_cast<const int *>(q.wblob);
+
+    auto decode = [&](int item, int &b, int &t0, int &nt, int &slice) {
+        slice = item % p.nslice;
+        const int r = item / p.nslice;
+        const int st = r % p.n_st;
+        b = r / p.n_st;
+        t0 = st * p.T;
+        nt = min(p.T, tiles_img - t0);
+    };
+
+    if (warp == 0) {
+        // ================================ weight producer ===================================
+        if (lane == 0) {
+            int bst = 0, bphase = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                int b, t0, nt, slice;
+                decode(item, b, t0, nt, slice);
+                for (int kc = 0; kc < p.nkc; ++kc) {
+                    mbar_wait(&bempty[bst], bphase ^ 1);
+                    mbar_arrive_expect_tx(&bfull[bst], w_chunk);
+                    const uint8_t *src = q.wblob + W_HDR + ((size_t)slice * p.nkc + kc) * w_chunk;
+                    asm volatile(
+                        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                        ::"r"(smem_u32(sW + bst * w_chunk)), "l"(src), "r"(w_chunk), "r"(smem_u32(&bfull[bst]))
+                        : "memory");
+                    if (++bst == NBST) { bst = 0; bphase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ========================================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_f16(128, p.N, 0);
+            const uint32_t b_lbo = p.N * 16;
+            int stage = 0, phase = 0, bst = 0, bphase = 0;
+            uint32_t tph = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                int b, t0, nt, slice;
+                decode(item, b, t0, nt, slice);
+                for (int kc = 0; kc < p.nkc; ++kc) {
+                    mbar_wait(&bfull[bst], bphase);
+                    tc_fence_after();
+                    const uint32_t w_hi = smem_u32(sW + bst * w_chunk), w_lo = w_hi + w_half;
+                    for (int t = 0; t < nt; ++t) {
+                        if (kc == 0) {
+                            mbar_wait(&tempty[t], ((tph >> t) & 1u) ^ 1u);
+                            tc_fence_after();
+                        }
+                        const uint32_t dacc = tmem_base + t * p.N;
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t a_hi = smem_u32(sA + stage * A_STAGE), a_lo = a_hi + A_HALF;
+#pragma unroll
+                        for (int j = 0; j < KOCT / 2; ++j) {
+                            const uint32_t ao = j * 2 * A_OCT_B, bo = j * 2 * b_lbo;
+                            const uint64_t dah = umma_smem_desc(a_hi + ao, A_OCT_B, 128);
+                            const uint64_t dal = umma_smem_desc(a_lo + ao, A_OCT_B, 128);
+                            const uint64_t dbh = umma_smem_desc(w_hi + bo, b_lbo, 128);
+                            const uint64_t dbl = umma_smem_desc(w_lo + bo, b_lbo, 128);
+                            umma_f16(dacc, dah, dbh, idesc, (kc | j) != 0);
+                            umma_f16(dacc, dah, dbl, idesc, 1);
+                            umma_f16(dacc, dal, dbh, idesc, 1);
+                        }
+                        umma_commit(&empty[stage]);
+                        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                        if (kc == p.nkc - 1) { umma_commit(&tfull[t]); tph ^= 1u << t; }
+                    }
+                    umma_commit(&bempty[bst]);
+                    if (++bst == NBST) { bst = 0; bphase ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ================================ epilogue ==========================================
+        const int e = threadIdx.x - 128;
+        const int quarter = warp & 3;
+        const float out_scale = ldexpf(1.f, -(p.sa_in + sw));
+        const float res_scale = 1.f;
+        const float so = ldexpf(1.f, p.sa_out);
+        uint32_t tph = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            int b, t0, nt, slice;
+            decode(item, b, t0, nt, slice);
+            const int o_base = slice * p.N;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int i = e; i < p.N; i += 128) sbias[i] = (q.bias && o_base + i < p.Cout) ? q.bias[o_base + i] : 0.f;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int t = 0; t < nt; ++t) {
+                const int tt = t0 + t;
+                const int y = (tt / p.tiles_x) * T_R + e / T_C, x = (tt % p.tiles_x) * T_C + e % T_C;
+                const bool ok = y < p.H && x < p.W;
+                mbar_wait(&tfull[t], (tph >> t) & 1u);
+                tph ^= 1u << t;
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + t * p.N;
+                epilogue_store_tile(q, p, taddr, b, y, x, ok, o_base, sbias, out_scale, res_scale, so);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[t]);
+            }
+        }
+    } else if (warp >= 8) {
+        // ================================ gather producers ==================================
+        const int g_tid = threadIdx.x - 256;             // 0..255
+        const int m = g_tid & 127;                       // pixel of the tile
+        const int oh = g_tid >> 7;                       // which octet pair of the chunk: octets 2*oh, 2*oh+1
+        const long long P = (long long)p.H * p.W;
+        int stage = 0, phase = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            int b, t0, nt, slice;
+            decode(item, b, t0, nt, slice);
+            const float *xb = d.x + (long long)b * d.xs_b;
+            const float *omb = d.om + (long long)b * 3 * d.dg * 9 * P;
+            for (int kc = 0; kc < p.nkc; ++kc) {
+                for (int t = 0; t < nt; ++t) {
+                    const int tt = t0 + t;
+                    const int y = (tt / p.tiles_x) * T_R + m / T_C, xx = (tt % p.tiles_x) * T_C + m % T_C;
+                    const bool inside = y < p.H && xx < p.W;
+                    const long long pp = (long long)y * p.W + xx;
+                    uint4 h_out[2], l_out[2];
+                    int last_pair = -1;
+                    int o0 = 0, o1 = 0, o2 = 0, o3 = 0;
+                    float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f, mk = 0.f;
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int ko = kc * KOCT + oh * 2 + u;          // global K octet
+                        __align__(16) __half h8[8];
+                        __align__(16) __half l8[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { h8[j] = __float2half_rn(0.f); l8[j] = h8[j]; }
+                        if (inside && ko < d.n_ko) {
+                            const int pair = ko / d.opp, oc = ko % d.opp;
+                            if (pair != last_pair) {
+                                last_pair = pair;
+                                const int g = pair / 9, tap = pair % 9;
+                                const int ki = tap / 3, kj = tap % 3;
+                                const int jj = g * 9 + tap;
+                                float off_h = omb[(long long)(2 * jj) * P + pp];
+                                float off_w = omb[(long long)(2 * jj + 1) * P + pp];
+                                const float mr = omb[(long long)(2 * d.dg * 9 + jj) * P + pp];
+                                float px = 0.f, py = 0.f;
+                                if (d.pre) {
+                                    const float *pq = d.pre + (((long long)b * 9 + tap) * P + pp) * 2;
+                                    px = pq[0];
+                                    py = pq[1];
+                                } else if (d.idx) {
+                                    const int sc = d.pre_scale;
+                                    const int ys = y - sc * ki, xs = xx - sc * kj;
+                                    if (ys >= 0 && xs >= 0) {
+                                        const int yy = ys / sc, xg = xs / sc;
+                                        if (yy < d.gh && xg < d.gw) {
+                                            const long long v = d.idx[((long long)b * d.gh + yy) * d.gw + xg];
+                                            px = (float)(sc * ((int)(v % d.ref_gw) - xg));
+                                            py = (float)(sc * ((int)(v / d.ref_gw) - yy));
+                                        }
+                                    }
+                                }
+                                off_h += py;
+                                off_w += px;
+                                const float h_im = (float)(y - 1 + ki) + off_h;
+                                const float w_im = (float)(xx - 1 + kj) + off_w;
+                                w0 = w1 = w2 = w3 = 0.f;
+                                o0 = o1 = o2 = o3 = 0;
+                                mk = 0.f;
+                                if (h_im > -1.f && w_im > -1.f && h_im < (float)p.H && w_im < (float)p.W) {
+                                    const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
+                                    const int h_high = h_low + 1, w_high = w_low + 1;
+                                    const float lh = h_im - h_low, lw = w_im - w_low;
+                                    const float hh = 1.f - lh, hw = 1.f - lw;
+                                    const bool tv = h_low >= 0, bv = h_high <= p.H - 1, lv = w_low >= 0, rv = w_high <= p.W - 1;
+                                    if (tv && lv) { o0 = (int)(h_low * d.xs_y + w_low * d.xs_x); w0 = hh * hw; }
+                                    if (tv && rv) { o1 = (int)(h_low * d.xs_y + w_high * d.xs_x); w1 = hh * lw; }
+                                    if (bv && lv) { o2 = (int)(h_high * d.xs_y + w_low * d.xs_x); w2 = lh * hw; }
+                                    if (bv && rv) { o3 = (int)(h_high * d.xs_y + w_high * d.xs_x); w3 = lh * lw; }
+                                    mk = 1.f / (1.f + expf(-mr));
+                                }
+                            }
+                            if (mk != 0.f) {
+                                const int c0 = (pair / 9) * d.cpg + oc * 8;          // first of the 8 channels (xs_c == 1)
+                                const float *xc = xb + c0;
+                                const float4 a0 = *reinterpret_cast<const float4 *>(xc + o0), a1 = *reinterpret_cast<const float4 *>(xc + o0 + 4);
+                                const float4 b0 = *reinterpret_cast<const float4 *>(xc + o1), b1 = *reinterpret_cast<const float4 *>(xc + o1 + 4);
+                                const float4 c0v = *reinterpret_cast<const float4 *>(xc + o2), c1v = *reinterpret_cast<const float4 *>(xc + o2 + 4);
+                                const float4 d0 = *reinterpret_cast<const float4 *>(xc + o3), d1 = *reinterpret_cast<const float4 *>(xc + o3 + 4);
+                                const float va[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                                const float vb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                                const float vc[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
+                                const float vd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const float v = (w0 * va[j] + w1 * vb[j] + w2 * vc[j] + w3 * vd[j]) * mk;
+                                    const __half hh = __float2half_rn(v);
+                                    h8[j] = hh;
+                                    l8[j] = __float2half_rn(v - __half2float(hh));
+                                }
+                            }
+                        }
+                        h_out[u] = *reinterpret_cast<const uint4 *>(h8);
+                        l_out[u] = *reinterpret_cast<const uint4 *>(l8);
+                    }
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t *s = sA + stage * A_STAGE;
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int oct = oh * 2 + u;
+                        *reinterpret_cast<uint4 *>(s + oct * A_OCT_B + m * 16) = h_out[u];
+                        *reinterpret_cast<uint4 *>(s + A_HALF + oct * A_OCT_B + m * 16) = l_out[u];
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full[stage]);
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+// blob: header | [slice][kc][hi|lo][octet 4][N][8], K ordered (g, tap, channel-in-group)
+__global__ void dcn_wpack_kernel(const float *__restrict__ w, int C, int Cout, int dg, int N, int nkc, int nslice,
+                                 uint8_t *__restrict__ blob) {
+    __shared__ int s_sw;
+    if (threadIdx.x == 0) {
+        const float a = __uint_as_float(reinterpret_cast<unsigned *>(blob)[1]);
+        int e = 0;
+        if (a > 0.f && isfinite(a)) frexpf(a, &e);
+        s_sw = 14 - e;
+        if (blockIdx.x == 0) reinterpret_cast<int *>(blob)[0] = s_sw;
+    }
+    __syncthreads();
+    const float S = ldexpf(1.f, s_sw);
+    const int cpg = C / dg, opp = cpg / 8, n_ko = (C / 8) * 9;
+    const long long total = (long long)nslice * nkc * 2 * KOCT * N * 8;
+    __half *dst = reinterpret_cast<__half *>(blob + W_HDR);
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(e & 7);
+        long long rest = e >> 3;
+        const int ol = (int)(rest % N); rest /= N;
+        const int oct = (int)(rest % KOCT); rest /= KOCT;
+        const int half = (int)(rest % 2); rest /= 2;
+        const int kc = (int)(rest % nkc);
+        const int slice = (int)(rest / nkc);
+        const int ko = kc * KOCT + oct, o = slice * N + ol;
+        float v = 0.f;
+        if (ko < n_ko && o < Cout) {
+            const int pair = ko / opp, oc = ko % opp, g = pair / 9, tap = pair % 9;
+            const int c = g * cpg + oc * 8 + j;
+            v = w[((size_t)o * C + c) * 9 + tap] * S;
+        }
+        const __half hh = __float2half_rn(v);
+        dst[e] = half ? __float2half_rn(v - __half2float(hh)) : hh;
+    }
+}
+
+__global__ void dcn_wamax_kernel(const float *__restrict__ w, int n, unsigned *__restrict__ bits) {
+    float m = 0.f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = fmaxf(m, fabsf(w[i]));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(bits, __float_as_uint(m));
+}
+
+static inline int d_pad16(int c) { return (c + 15) / 16 * 16; }
+// the gather is the expensive side, so one CTA owns ALL output channels (N up to 256) instead of
+// re-gathering per 64-wide slice; tiles per item shrink so that T*N <= 512 TMEM columns
+static inline int d_slice_n(int cout) { return d_pad16(cout); }
+static inline int d_n_slice(int cout) { (void)cout; return 1; }
+static inline int d_nkc(int C) { return ((C / 8) * 9 + KOCT - 1) / KOCT; }
+
+}  // namespace c2m
+
+using namespace c2m;
+
+extern "C" int c2m_dcn_tc_supported(int C, int Cout, int dg) {
+    return (C > 0 && Cout > 0 && Cout <= 256 && dg > 0 && C % dg == 0 && (C / dg) % 8 == 0) ? 1 : 0;
+}
+
+extern "C" size_t c2m_dcn_tc_packed_weight_bytes(int C, int Cout, int dg) {
+    if (!c2m_dcn_tc_supported(C, Cout, dg)) return 0;
+    return (size_t)W_HDR + (size_t)d_n_slice(Cout) * d_nkc(C) * 2 * KOCT * d_slice_n(Cout) * 16;
+}
+
+extern "C" int c2m_dcn_tc_pack_weights_f32(const float *w, int C, int Cout, int dg, void *packed, c2m_stream_t stream) {
+    C2M_CHECK_ARG(w && packed, "dcn_tc_pack_weights: null pointer");
+    C2M_CHECK_ARG(c2m_dcn_tc_supported(C, Cout, dg), "dcn_tc_pack_weights: C=%d dg=%d unsupported (C/dg must be a multiple of 8)", C, dg);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    C2M_CUDA(cudaMemsetAsync(packed, 0, W_HDR, st));
+    const int n = Cout * C * 9;
+    dcn_wamax_kernel<<<ceil_div(n, 1024) > 64 ? 64 : ceil_div(n, 1024), 256, 0, st>>>(w, n, reinterpret_cast<unsigned *>(packed) + 1);
+    C2M_LAUNCH_CHECK("dcn_wamax_kernel");
+    const int N = d_slice_n(Cout), nkc = d_nkc(C), ns = d_n_slice(Cout);
+    const long long total = (long long)ns * nkc * 2 * KOCT * N * 8;
+    const int blocks = (int)((total + 255) / 256 > 592 ? 592 : (total + 255) / 256);
+    dcn_wpack_kernel<<<blocks, 256, 0, st>>>(w, C, Cout, dg, N, nkc, ns, reinterpret_cast<uint8_t *>(packed));
+    C2M_LAUNCH_CHECK("dcn_wpack_kernel");
+    return C2M_OK;
+}
+
+extern "C" int c2m_dcn_v2_fused_tc(const c2m_dcn_tc_args *a, c2m_stream_t stream) {
+    C2M_CHECK_ARG(a && a->x && a->om && a->packed_w, "dcn_v2_fused_tc: null pointer");
+    C2M_CHECK_ARG(a->B > 0 && a->H > 0 && a->W > 0, "dcn_v2_fused_tc: bad shape");
+    C2M_CHECK_ARG(c2m_dcn_tc_supported(a->C, a->Cout, a->dg), "dcn_v2_fused_tc: C=%d dg=%d unsupported", a->C, a->dg);
+    C2M_CHECK_ARG(a->xs_c == 1, "dcn_v2_fused_tc: input must be channels-last (channel stride 1, got %lld)", a->xs_c);
+    C2M_CHECK_ARG((a->xs_x % 4) == 0 && (a->xs_y % 4) == 0 && (a->xs_b % 4) == 0 && ((uintptr_t)a->x % 16) == 0,
+                  "dcn_v2_fused_tc: input rows must be 16-byte aligned");
+    C2M_CHECK_ARG(!(a->pre == nullptr && a->idx != nullptr) || (a->gh > 0 && a->gw > 0 && a->ref_gw > 0 && a->pre_scale > 0),
+                  "dcn_v2_fused_tc: idx given without a valid grid/scale");
+    C2M_CHECK_ARG((a->out_hi == nullptr) == (a->out_lo == nullptr) && (a->out_hi || a->out_f32), "dcn_v2_fused_tc: bad outputs");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    ConvParams p = {};
+    p.B = a->B; p.H = a->H; p.W = a->W;
+    p.nkc = d_nkc(a->C); p.nkc_a = p.nkc;
+    p.Cout = a->Cout; p.N = d_slice_n(a->Cout); p.nslice = d_n_slice(a->Cout);
+    p.tiles_x = ceil_div(a->W, T_C); p.tiles_y = ceil_div(a->H, T_R);
+    p.T = 512 / p.N < MAXT ? 512 / p.N : MAXT;
+    p.n_st = ceil_div(p.tiles_x * p.tiles_y, p.T);
+    p.act = a->lrelu ? 2 : 0;
+    p.sa_in = 0; p.sa_res = 0; p.sa_out = a->sa_out;
+    p.ps = 0;
+    p.C8out = (a->Cout + 7) / 8; p.Hout = a->H; p.Wout = a->W;
+    p.os_b = a->os_b; p.os_c = a->os_c; p.os_y = a->os_y; p.os_x = a->os_x;
+    ConvPtrs q = {};
+    q.wblob = reinterpret_cast<const uint8_t *>(a->packed_w);
+    q.bias = a->bias;
+    q.out_hi = reinterpret_cast<__half *>(a->out_hi); q.out_lo = reinterpret_cast<__half *>(a->out_lo);
+    q.out_f32 = a->out_f32;
+    DcnTc d;
+    d.x = a->x; d.xs_b = a->xs_b; d.xs_c = a->xs_c; d.xs_y = a->xs_y; d.xs_x = a->xs_x;
+    d.om = a->om; d.pre = a->pre; d.idx = reinterpret_cast<const long long *>(a->idx);
+    d.gh = a->gh; d.gw = a->gw; d.ref_gw = a->ref_gw; d.pre_scale = a->pre_scale;
+    d.C = a->C; d.dg = a->dg; d.cpg = a->C / a->dg; d.opp = d.cpg / 8; d.n_ko = (a->C / 8) * 9;
+    const size_t smem = (size_t)NBST * 2 * KOCT * p.N * 16 + NSTAGE * A_STAGE + 4096;
+    C2M_CUDA(cudaFuncSetAttribute(dcn_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, sms = 0;
+    C2M_CUDA(cudaGetDevice(&dev));
+    C2M_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int n_items = a->B * p.n_st * p.nslice;
+    dcn_umma_kernel<<<n_items < sms ? n_items : sms, 512, smem, st>>>(q, p, d);
+    C2M_LAUNCH_CHECK("dcn_umma_kernel");
+    return C2M_OK;
+}

@@ -1,0 +1,135 @@
+// Shared pieces of the tcgen05 implicit-GEMM kernels (plain 3x3 conv, deformable conv):
+// parameter blocks and the epilogue that turns one 128-pixel x N-column TMEM accumulator into
+// packed-split (PSA) and / or strided fp32 output with bias, activation, residuals and an optional
+// fused PixelShuffle(2).
+#pragma once
+#include "c2m_common.cuh"
+
+namespace c2m {
+
+constexpr int UC_NMAX = 64;      // output channels per CTA slice
+
+struct ConvParams {
+    int B, H, W;
+    int nkc_a, nkc;           // K chunks taken from input 1 / in total (input 2 supplies the rest)
+    int Cout, N, nslice;      // real couts, couts per CTA slice (multiple of 16), slices; slice s starts at s*N
+    int tiles_x, tiles_y, T, n_st;   // tile grid, tiles per item, super-tiles per image
+    int act;                  // 0 none, 1 relu, 2 leaky relu 0.1
+    int sa_in, sa_res, sa_out;
+    int ps;                   // 0 or 2: PixelShuffle(2) applied to the PSA output
+    int C8out, Hout, Wout;    // geometry of the PSA output tensor
+    long long os_b, os_c, os_y, os_x;   // fp32 output element strides
+};
+struct ConvPtrs {
+    const uint8_t *wblob;
+    const float *bias;
+    const __half *res_hi, *res_lo, *res2_hi, *res2_lo;
+    __half *out_hi, *out_lo;
+    float *out_f32;
+    const float *add_f32;
+};
+
+// One thread = one output pixel (TMEM lane); `taddr` already carries the lane quarter and the
+// accumulator's first column.
+__device__ __forceinline__ void epilogue_store_tile(const ConvPtrs &q, const ConvParams &p, uint32_t taddr, int b, int y,
+                                                    int x, bool ok, int o_base, const float *sbias, float out_scale,
+                                                    float res_scale, float so) {
+                    for (int c0 = 0; c0 < p.N; c0 += 32) {
+                        uint32_t reg[32];
+                        if (p.N - c0 >= 32) {
+                            tmem_ld_32x32(taddr + c0, reg);
+                        } else {   // 16-column tail
+                            asm volatile(
+                                "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                                : "=r"(reg[0]), "=r"(reg[1]), "=r"(reg[2]), "=r"(reg[3]), "=r"(reg[4]), "=r"(reg[5]),
+                                  "=r"(reg[6]), "=r"(reg[7]), "=r"(reg[8]), "=r"(reg[9]), "=r"(reg[10]), "=r"(reg[11]),
+                                  "=r"(reg[12]), "=r"(reg[13]), "=r"(reg[14]), "=r"(reg[15])
+                                : "r"(taddr + c0)
+                                : "memory");
+                        }
+                        tmem_ld_wait();
+                        if (!ok) continue;
+                        const int ncol = min(32, p.N - c0);
+                        float v[32];
+    #pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            float a = fmaf(__uint_as_float(reg[j]), out_scale, sbias[c0 + j]);
+                            if (p.act == 1) a = fmaxf(a, 0.f);
+                            else if (p.act == 2) a = a > 0.f ? a : a * 0.1f;
+                            v[j] = (j < ncol && o_base + c0 + j < p.Cout) ? a : 0.f;
+                        }
+                        if (q.out_f32) {
+    #pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const int o = o_base + c0 + j;
+                                if (j < ncol && o < p.Cout) {
+                                    const long long oi = b * p.os_b + o * p.os_c + y * p.os_y + x * p.os_x;
+                                    q.out_f32[oi] = q.add_f32 ? v[j] + q.add_f32[oi] : v[j];
+                                }
+                            }
+                        }
+                        if (q.out_hi && p.ps == 0) {
+    #pragma unroll
+                            for (int o8 = 0; o8 < 4; ++o8) {
+                                const int oct = (o_base + c0) / 8 + o8;
+                                if (o8 * 8 >= ncol || oct >= p.C8out) break;
+                                const size_t off = ((((size_t)b * p.C8out + oct) * p.H + y) * p.W + x) * 8;
+                                float r8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                                if (q.res_hi) {
+                                    const uint4 rh = *reinterpret_cast<const uint4 *>(q.res_hi + off);
+                                    const uint4 rl = *reinterpret_cast<const uint4 *>(q.res_lo + off);
+                                    const __half *hh = reinterpret_cast<const __half *>(&rh);
+                                    const __half *ll = reinterpret_cast<const __half *>(&rl);
+    #pragma unroll
+                                    for (int j = 0; j < 8; ++j) r8[j] = (__half2float(hh[j]) + __half2float(ll[j])) * res_scale;
+                                }
+                                if (q.res2_hi) {
+                                    const uint4 rh = *reinterpret_cast<const uint4 *>(q.res2_hi + off);
+                                    const uint4 rl = *reinterpret_cast<const uint4 *>(q.res2_lo + off);
+                                    const __half *hh = reinterpret_cast<const __half *>(&rh);
+                                    const __half *ll = reinterpret_cast<const __half *>(&rl);
+    #pragma unroll
+                                    for (int j = 0; j < 8; ++j) r8[j] += (__half2float(hh[j]) + __half2float(ll[j])) * res_scale;
+                                }
+                                __align__(16) __half h8[8];
+                                __align__(16) __half l8[8];
+    #pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const int o = o_base + c0 + o8 * 8 + j;
+                                    const float vs = (o < p.Cout ? v[o8 * 8 + j] + r8[j] : 0.f) * so;
+                                    const __half hh = __float2half_rn(vs);
+                                    h8[j] = hh;
+                                    l8[j] = __float2half_rn(vs - __half2float(hh));
+                                }
+                                *reinterpret_cast<uint4 *>(q.out_hi + off) = *reinterpret_cast<const uint4 *>(h8);
+                                *reinterpret_cast<uint4 *>(q.out_lo + off) = *reinterpret_cast<const uint4 *>(l8);
+                            }
+                        }
+                        if (q.out_hi && p.ps == 2) {
+                            // PixelShuffle(2): conv channel o = 4c + 2i + j  ->  out[c][2y+i][2x+j]
+                            // the 32 columns at c0 hold c = (o_base+c0)/4 .. +7  = exactly one output octet
+                            const int oct = (o_base + c0) / 32;
+                            if (oct < p.C8out && ncol == 32) {
+    #pragma unroll
+                                for (int ij = 0; ij < 4; ++ij) {
+                                    const size_t off = ((((size_t)b * p.C8out + oct) * p.Hout + 2 * y + (ij >> 1)) * p.Wout +
+                                                        2 * x + (ij & 1)) * 8;
+                                    __align__(16) __half h8[8];
+                                    __align__(16) __half l8[8];
+    #pragma unroll
+                                    for (int c = 0; c < 8; ++c) {
+                                        const float vs = v[c * 4 + ij] * so;
+                                        const __half hh = __float2half_rn(vs);
+                                        h8[c] = hh;
+                                        l8[c] = __float2half_rn(vs - __half2float(hh));
+                                    }
+                                    *reinterpret_cast<uint4 *>(q.out_hi + off) = *reinterpret_cast<const uint4 *>(h8);
+                                    *reinterpret_cast<uint4 *>(q.out_lo + off) = *reinterpret_cast<const uint4 *>(l8);
+                                }
+                            }
+                        }
+                    }
+}
+
+}  // namespace c2m

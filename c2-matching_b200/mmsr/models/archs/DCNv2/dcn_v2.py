@@ -7,6 +7,7 @@ sampling, contraction, bias, optional LeakyReLU) in ONE kernel and drops the ref
 host-synchronising `offset_mean > 100` check (dcn_v2.py:247-250) unless `debug_offset_check`."""
 import logging
 import math
+import os
 
 import _ext as _backend
 import torch
@@ -118,9 +119,10 @@ class DCN_sep_pre_multi_offset(_WithOffsetConv):
             x, feat = x[0], x[1]
         return self.fused_tail(x, self.conv_offset_mask(feat), pre_offset, lrelu_slope, channels_last_out)
 
-    def fused_tail(self, x, om, pre_offset, lrelu_slope=1.0, channels_last_out=False):
+    def fused_tail(self, x, om, pre_offset, lrelu_slope=1.0, channels_last_out=False, want_psa=False):
         """Everything after the conv_offset_mask convolution (dcn_v2.py:230-253), one kernel.
-        `om`: raw conv_offset_mask output [B, 3*dg*9, H, W] fp32."""
+        `om`: raw conv_offset_mask output [B, 3*dg*9, H, W] fp32.  With want_psa the result is
+        returned in the packed-split layout (tensor-core kernel only)."""
         if self.stride != (1, 1) or self.dilation != (1, 1):
             raise NotImplementedError('fused pre-offset DCN supports stride 1 / dilation 1 (all C2-Matching uses)')
         if self.debug_offset_check:
@@ -128,10 +130,14 @@ class DCN_sep_pre_multi_offset(_WithOffsetConv):
             if mean > 100:
                 logger.warning(f'Offset mean is {mean}, larger than 100.')
         idx = getattr(pre_offset, 'max_idx', None)
-        if idx is not None:      # ScaleOffsets handle from CorrespondenceGenerationArch: no pyramid in HBM
-            return _ops.dcn_v2_fused_forward(x, om, self.weight, self.bias, self.deformable_groups, idx=idx,
-                                             pre_scale=pre_offset.scale, ref_gw=pre_offset.ref_gw,
-                                             lrelu_slope=lrelu_slope, channels_last_out=channels_last_out)
-        return _ops.dcn_v2_fused_forward(x, om, self.weight, self.bias, self.deformable_groups,
-                                         pre_offset=pre_offset, lrelu_slope=lrelu_slope,
-                                         channels_last_out=channels_last_out)
+        kw = dict(idx=idx, pre_scale=pre_offset.scale, ref_gw=pre_offset.ref_gw) if idx is not None else \
+            dict(pre_offset=pre_offset)          # ScaleOffsets handle: no offset pyramid in HBM
+        tc = (self.kernel_size == (3, 3) and self.padding == (1, 1) and lrelu_slope in (1.0, 0.1) and
+              os.environ.get('C2M_DCN_TC', '1') != '0' and
+              _ops.dcn_tc_supported(self.in_channels, self.out_channels, self.deformable_groups))
+        if tc:
+            return _ops.dcn_v2_fused_tc(x, om, self.weight, self.bias, self.deformable_groups, lrelu=lrelu_slope == 0.1,
+                                        psa_out=want_psa, out_f32=not want_psa, channels_last_out=channels_last_out, **kw)
+        out = _ops.dcn_v2_fused_forward(x, om, self.weight, self.bias, self.deformable_groups,
+                                        lrelu_slope=lrelu_slope, channels_last_out=channels_last_out, **kw)
+        return _ops.psa_from_f32(out) if want_psa else out

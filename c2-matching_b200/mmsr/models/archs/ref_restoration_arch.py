@@ -83,8 +83,8 @@ class DynamicAggregationRestoration(nn.Module):
             off = arch_util.conv_psa(getattr(self, f'{size}_offset_conv1'), xp, act='lrelu', x2=refp)
             off = arch_util.conv_psa(getattr(self, f'{size}_offset_conv2'), off, act='lrelu')
             om = arch_util.conv_psa(dyn.conv_offset_mask, off, psa_out=False, out_f32=True)
-            swapped = dyn.fused_tail(ref, om, self._pre(pre_offset, key), lrelu_slope=0.1)
-            h = arch_util.conv_psa(getattr(self, f'head_{size}')[0], xp, act='lrelu', x2=ops.psa_from_f32(swapped))
+            swapped = dyn.fused_tail(ref, om, self._pre(pre_offset, key), lrelu_slope=0.1, want_psa=True)
+            h = arch_util.conv_psa(getattr(self, f'head_{size}')[0], xp, act='lrelu', x2=swapped)
             h = arch_util.resblocks_psa(getattr(self, f'body_{size}'), h, final_residual2=xp)
             tail = getattr(self, f'tail_{size}')
             if size != 'large':

@@ -98,8 +98,9 @@ def run_trunk(trunk, x, taps=(), want_last_f32=True):
             need_psa = isinstance(nxt, nn.Conv2d) or out_name in taps
             if xp is None:
                 xp = ops.psa_from_f32(xf)
+            # tapped features feed the DCN sampler, which gathers 8-channel octets: keep them channels-last
             r = ops.conv3x3_psa(xp, layer.weight, layer.bias, act='relu' if has_relu else None, psa_out=need_psa,
-                                out_f32=need_f32)
+                                out_f32=need_f32, channels_last=out_name in taps)
             if need_psa and need_f32:
                 xp, xf = r
                 arch_util.attach_psa(xf, xp)

@@ -141,6 +141,28 @@ int c2m_psa_to_f32(const void *hi, const void *lo, int B, int C, int H, int W, i
                    long long os_b, long long os_c, long long os_y, long long os_x, c2m_stream_t stream);
 int c2m_conv3x3(const c2m_conv3x3_args *args, c2m_stream_t stream);
 
+/* --- DCNv2 forward on tcgen05 (3x3 / stride 1 / pad 1 / dilation 1, C/dg % 8 == 0, Cout <= 256) ---
+ * Same contract as c2m_dcn_v2_fused_forward_f32 (raw conv_offset_mask output `om`, pre-offsets from
+ * `pre` or rebuilt from `idx`), but the contraction runs as a split-fp16 tensor-core GEMM fed by
+ * gather warps; the input must be channels-last (xs_c == 1).  Outputs: PSA (out_hi/out_lo) and / or
+ * strided fp32; `lrelu` != 0 applies LeakyReLU(0.1).  Weights are packed once with
+ * c2m_dcn_tc_pack_weights_f32 into c2m_dcn_tc_packed_weight_bytes(C, Cout, dg) bytes.
+ */
+typedef struct {
+    const float *x; long long xs_b, xs_c, xs_y, xs_x;
+    const float *om; const float *pre; const int64_t *idx;
+    int gh, gw, ref_gw, pre_scale;
+    int B, C, H, W, Cout, dg;
+    const void *packed_w; const float *bias; int lrelu;
+    void *out_hi, *out_lo; int sa_out;
+    float *out_f32; long long os_b, os_c, os_y, os_x;
+} c2m_dcn_tc_args;
+
+int c2m_dcn_tc_supported(int C, int Cout, int dg);
+size_t c2m_dcn_tc_packed_weight_bytes(int C, int Cout, int dg);
+int c2m_dcn_tc_pack_weights_f32(const float *w, int C, int Cout, int dg, void *packed, c2m_stream_t stream);
+int c2m_dcn_v2_fused_tc(const c2m_dcn_tc_args *args, c2m_stream_t stream);
+
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 unsigned long long c2m_launch_count(void);
 

@@ -416,3 +416,36 @@ def test_fast_conv_path_equals_cudnn_path(monkeypatch):
     assert flips <= 2
     if flips == 0:
         _rel_ok(sr_fast, sr_slow, 1e-3)
+
+
+@pytest.mark.parametrize('cfg', [(1, 64, 64, 8, 10, 12, 2), (2, 16, 16, 2, 20, 9, 1), (1, 128, 128, 8, 9, 9, 2),
+                                 (1, 256, 256, 8, 20, 20, 1), (1, 32, 48, 4, 18, 11, 1)],
+                         ids=lambda c: f'C{c[1]}to{c[2]}_dg{c[3]}')
+def test_dcn_tensor_core_vs_literal_oracle(cfg):
+    """tcgen05 DCN (gather warps + split-fp16 contraction) == the literal C restatement of the
+    reference kernel (fp64 accumulation), pre-offsets rebuilt from the index map, LeakyReLU fused,
+    PSA and fp32 outputs identical."""
+    import c2m_b200 as c2m
+    from c2m_b200 import ops
+    B, C, cout, dg, gh, gw, sc = cfg
+    H, W = sc * (gh + 2), sc * (gw + 2)
+    idx = torch.from_numpy(np.random.default_rng(5).integers(0, gh * gw, (B, gh, gw))).to(DEV)
+    x = seeding.randn(61, (B, C, H, W)).to(DEV)
+    om = seeding.randn(62, (B, 27 * dg, H, W), 0.7).to(DEV)
+    wgt = seeding.randn(63, (cout, C, 3, 3), 0.1).to(DEV)
+    bias = seeding.randn(64, (cout,)).to(DEV)
+    gp, gf = ops.dcn_v2_fused_tc(x, om, wgt, bias, dg, idx=idx, pre_scale=sc, lrelu=True, psa_out=True, out_f32=True)
+    pre = c2m.offset_pyramid(idx, sc)
+    n = dg * 9
+    off = om[:, :2 * n].clone()
+    pr = pre.repeat(1, dg, 1, 1, 1)
+    off[:, 0::2] += pr[..., 1]
+    off[:, 1::2] += pr[..., 0]
+    lit = c_oracle.dcn_v2_forward(x.cpu(), wgt.cpu(), bias.cpu(), off.cpu(), torch.sigmoid(om[:, 2 * n:]).cpu(), dg=dg, acc64=True)
+    lit = F.leaky_relu(lit, 0.1)
+    _rel_ok(gf.cpu(), lit, 2e-5)
+    assert float((ops.psa_to_f32(gp) - gf).abs().max()) <= 1e-6 * float(lit.abs().max())
+    # same through the pre_offset tensor instead of idx, no activation
+    gf2 = ops.dcn_v2_fused_tc(x, om, wgt, bias, dg, pre_offset=pre, lrelu=False)
+    ff = c2m.dcn_v2_fused_forward(x, om, wgt, bias, dg, pre_offset=pre)
+    _rel_ok(gf2, ff, 2e-5)

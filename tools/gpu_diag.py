@@ -270,12 +270,71 @@ def conv_diag():
             traceback.print_exc()
 
 
+def dcntc_diag():
+    section('DCN tensor-core vs FFMA kernel / oracle')
+    from c2m_b200 import ops
+    for (B, C, cout, dg, gh, gw, sc) in ((1, 64, 64, 8, 10, 12, 2), (2, 16, 16, 2, 20, 9, 1), (1, 128, 128, 8, 9, 9, 2), (1, 256, 256, 8, 20, 20, 1), (1, 32, 48, 4, 18, 11, 1)):
+        try:
+            H, W = sc * (gh + 2), sc * (gw + 2)
+            idx = torch.from_numpy(np.random.default_rng(5).integers(0, gh * gw, (B, gh, gw))).to(dev)
+            x = seeding.randn(61, (B, C, H, W)).to(dev)
+            om = seeding.randn(62, (B, 27 * dg, H, W), 0.7).to(dev)
+            wgt = seeding.randn(63, (cout, C, 3, 3), 0.1).to(dev)
+            bias = seeding.randn(64, (cout,)).to(dev)
+            want = c2m.dcn_v2_fused_forward(x, om, wgt, bias, dg, idx=idx, pre_scale=sc, lrelu_slope=0.1)
+            gp, gf = ops.dcn_v2_fused_tc(x, om, wgt, bias, dg, idx=idx, pre_scale=sc, lrelu=True, psa_out=True, out_f32=True)
+            torch.cuda.synchronize()
+            print(f'B{B} C{C}->{cout} dg{dg} {H}x{W}: tc vs ffma max diff {float((gf - want).abs().max()):.3e} (scale {float(want.abs().max()):.2f}); psa vs f32 {float((ops.psa_to_f32(gp) - gf).abs().max()):.2e}', flush=True)
+            # vs the literal C oracle (fp64 accumulation)
+            pre = c2m.offset_pyramid(idx, sc)
+            n = dg * 9
+            off = om[:, :2 * n].clone()
+            pr = pre.repeat(1, dg, 1, 1, 1)
+            off[:, 0::2] += pr[..., 1]
+            off[:, 1::2] += pr[..., 0]
+            lit = c_oracle.dcn_v2_forward(x.cpu(), wgt.cpu(), bias.cpu(), off.cpu(), torch.sigmoid(om[:, 2 * n:]).cpu(), dg=dg, acc64=True)
+            lit = torch.nn.functional.leaky_relu(lit, 0.1)
+            print(f'     tc vs literal oracle {float((gf.cpu() - lit).abs().max()):.3e}; ffma vs oracle {float((want.cpu() - lit).abs().max()):.3e}', flush=True)
+        except Exception:
+            traceback.print_exc()
+    section('DCN timing B=4 (tc vs ffma)')
+    for (C, H) in ((256, 160), (128, 320), (64, 640)):
+        try:
+            B = 4
+            gh = gw = 158
+            sc = H // 160
+            idx = torch.randint(0, gh * gw, (B, gh, gw), device=dev)
+            x = torch.randn(B, C, H, H, device=dev).contiguous(memory_format=torch.channels_last)
+            om = torch.randn(B, 216, H, H, device=dev)
+            wgt = torch.randn(C, C, 3, 3, device=dev) * 0.05
+            bias = torch.randn(C, device=dev)
+
+            def t(fn, n=5):
+                for _ in range(2):
+                    fn()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(n):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                return e0.elapsed_time(e1) / n
+            ms_tc = t(lambda: ops.dcn_v2_fused_tc(x, om, wgt, bias, 8, idx=idx, pre_scale=sc, lrelu=True, psa_out=True, out_f32=False))
+            ms_ff = t(lambda: c2m.dcn_v2_fused_forward(x, om, wgt, bias, 8, idx=idx, pre_scale=sc, lrelu_slope=0.1), 3)
+            print(f'C={C} H={H}: tc {ms_tc:.3f} ms, ffma {ms_ff:.3f} ms', flush=True)
+        except Exception:
+            traceback.print_exc()
+
+
 if __name__ == '__main__':
     print(torch.cuda.get_device_name(0), torch.__version__)
     c_oracle.build()
     which = sys.argv[1:] or ['corr', 'big', 'offsets', 'dcn']
     if 'conv' in which:
         conv_diag()
+    if 'dcntc' in which:
+        dcntc_diag()
     if 'corr' in which:
         corr_diag()
     if 'offsets' in which:
