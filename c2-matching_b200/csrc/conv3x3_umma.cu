@@ -66,7 +66,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_img = p.tiles_x * p.tiles_y;
     const int n_items = p.B * p.n_st * p.nslice;
-    const uint32_t need_cols = (uint32_t)p.N * p.T;
+    const uint32_t need_cols = 2u * p.N * p.T;            // stacked accumulators: 2N columns per tile
     const uint32_t tmem_cols = need_cols <= 32 ? 32 : need_cols <= 64 ? 64 : need_cols <= 128 ? 128
                                : need_cols <= 256 ? 256 : 512;
 
@@ -140,8 +140,11 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
     } else if (warp == 1) {
         // ================================ MMA issuer ========================================
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_f16(128, p.N, 0);
-            const uint32_t b_lbo = p.N * 16;                 // next channel octet of the weights
+            // B = [W_hi | W_lo] stacked along N (2N rows per octet): an N = 64 MMA occupies the tensor
+            // pipe as long as an N = 128 one (A-operand fetch bound, ncu: pipe_tc 81 % vs math 40 %),
+            // so x_hi*[W_hi|W_lo] + x_lo*[W_hi|W_lo] is 2 MMAs per K step instead of 3 (and exact)
+            const uint32_t idesc = umma_idesc_f16(128, 2 * p.N, 0);
+            const uint32_t b_lbo = 2 * p.N * 16;             // next channel octet of the weights
             int stage = 0, phase = 0, bst = 0, bphase = 0;
             uint32_t tph = 0;                                  // per-accumulator phase bits
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -150,13 +153,13 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                 for (int kc = 0; kc < p.nkc; ++kc) {
                     mbar_wait(&bfull[bst], bphase);
                     tc_fence_after();
-                    const uint32_t w_hi = smem_u32(sW + bst * w_chunk), w_lo = w_hi + w_half;
+                    const uint32_t w_st = smem_u32(sW + bst * w_chunk);
                     for (int t = 0; t < nt; ++t) {
                         if (kc == 0) {
                             mbar_wait(&tempty[t], ((tph >> t) & 1u) ^ 1u);
                             tc_fence_after();
                         }
-                        const uint32_t d = tmem_base + t * p.N;
+                        const uint32_t d = tmem_base + t * 2 * p.N;
                         mbar_wait(&full[stage], phase);
                         tc_fence_after();
                         const uint32_t a_hi = smem_u32(sA + stage * A_STAGE), a_lo = a_hi + A_HALF;
@@ -169,11 +172,9 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                                 const uint32_t ao = toff + j * 2 * A_OCT_B, bo = wtap + j * 2 * b_lbo;
                                 const uint64_t dah = umma_smem_desc(a_hi + ao, A_OCT_B, ROW_B);
                                 const uint64_t dal = umma_smem_desc(a_lo + ao, A_OCT_B, ROW_B);
-                                const uint64_t dbh = umma_smem_desc(w_hi + bo, b_lbo, 128);
-                                const uint64_t dbl = umma_smem_desc(w_lo + bo, b_lbo, 128);
-                                umma_f16(d, dah, dbh, idesc, (kc | tap | j) != 0);
-                                umma_f16(d, dah, dbl, idesc, 1);
-                                umma_f16(d, dal, dbh, idesc, 1);
+                                const uint64_t db = umma_smem_desc(w_st + bo, b_lbo, 128);
+                                umma_f16(d, dah, db, idesc, (kc | tap | j) != 0);
+                                umma_f16(d, dal, db, idesc, 1);
                             }
                         }
                         umma_commit(&empty[stage]);
@@ -207,7 +208,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                 mbar_wait(&tfull[t], (tph >> t) & 1u);
                 tph ^= 1u << t;
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + t * p.N;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + t * 2 * p.N;
                 epilogue_store_tile(q, p, taddr, b, y, x, ok, o_base, sbias, out_scale, res_scale, so);
                 tc_fence_before();
                 __syncwarp();
@@ -292,7 +293,8 @@ __global__ void wamax_kernel(const float *__restrict__ w, int n, unsigned *__res
     if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(bits, __float_as_uint(m));
 }
 
-// blob: [int sw][unsigned amax_bits]...pad to 256 B | [slice][kc][hi|lo][tap][octet][N][8] fp16
+// blob: [int sw][unsigned amax_bits]...pad to 256 B | [slice][kc][tap][octet][hi|lo][N][8] fp16
+// (hi and lo rows of one octet are adjacent: together they are the 2N-row stacked B operand)
 __global__ void wpack_kernel(const float *__restrict__ w, int Cin, int Cout, int N, int nkc, int nslice,
                              uint8_t *__restrict__ blob) {
     __shared__ int s_sw;
@@ -311,9 +313,9 @@ __global__ void wpack_kernel(const float *__restrict__ w, int Cin, int Cout, int
         const int j = (int)(e & 7);
         long long rest = e >> 3;
         const int ol = (int)(rest % N); rest /= N;
+        const int half = (int)(rest % 2); rest /= 2;
         const int oct = (int)(rest % KOCT); rest /= KOCT;
         const int tap = (int)(rest % 9); rest /= 9;
-        const int half = (int)(rest % 2); rest /= 2;
         const int kc = (int)(rest % nkc);
         const int slice = (int)(rest / nkc);
         const int c = (kc * KOCT + oct) * 8 + j, o = slice * NMAX + ol;
@@ -434,7 +436,8 @@ extern "C" int c2m_conv3x3(const c2m_conv3x3_args *a, c2m_stream_t stream) {
     if (a->Cin2) p.nkc_a = a->Cin / (KOCT * 8);
     p.Cout = a->Cout; p.N = slice_n(a->Cout); p.nslice = n_slice(a->Cout);
     p.tiles_x = ceil_div(a->W, T_C); p.tiles_y = ceil_div(a->H, T_R);
-    p.T = MAXT;
+    p.T = 512 / (2 * p.N) < MAXT ? 512 / (2 * p.N) : MAXT;
+    p.stacked = 1;
     p.n_st = ceil_div(p.tiles_x * p.tiles_y, p.T);
     p.act = a->act; p.sa_in = a->sa_in; p.sa_res = a->sa_res; p.sa_out = a->sa_out;
     p.ps = a->pixel_shuffle;

@@ -17,6 +17,7 @@ struct ConvParams {
     int act;                  // 0 none, 1 relu, 2 leaky relu 0.1
     int sa_in, sa_res, sa_out;
     int ps;                   // 0 or 2: PixelShuffle(2) applied to the PSA output
+    int stacked;              // 1: accumulator has 2N columns, value = col[c] + col[N + c]
     int C8out, Hout, Wout;    // geometry of the PSA output tensor
     long long os_b, os_c, os_y, os_x;   // fp32 output element strides
 };
@@ -48,7 +49,29 @@ __device__ __forceinline__ void epilogue_store_tile(const ConvPtrs &q, const Con
                                 : "r"(taddr + c0)
                                 : "memory");
                         }
-                        tmem_ld_wait();
+                        if (p.stacked) {
+                            // B operand was [W_hi | W_lo] stacked along N: columns c and N + c hold the
+                            // (x * w_hi) and (x * w_lo) partial sums of output channel c
+                            uint32_t reg2[32];
+                            if (p.N - c0 >= 32) {
+                                tmem_ld_32x32(taddr + p.N + c0, reg2);
+                            } else {
+                                asm volatile(
+                                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                                    : "=r"(reg2[0]), "=r"(reg2[1]), "=r"(reg2[2]), "=r"(reg2[3]), "=r"(reg2[4]), "=r"(reg2[5]),
+                                      "=r"(reg2[6]), "=r"(reg2[7]), "=r"(reg2[8]), "=r"(reg2[9]), "=r"(reg2[10]), "=r"(reg2[11]),
+                                      "=r"(reg2[12]), "=r"(reg2[13]), "=r"(reg2[14]), "=r"(reg2[15])
+                                    : "r"(taddr + p.N + c0)
+                                    : "memory");
+                            }
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                reg[j] = __float_as_uint(__uint_as_float(reg[j]) + __uint_as_float(reg2[j]));
+                        } else {
+                            tmem_ld_wait();
+                        }
                         if (!ok) continue;
                         const int ncol = min(32, p.N - c0);
                         float v[32];
