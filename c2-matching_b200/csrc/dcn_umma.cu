@@ -187,116 +187,147 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
         }
     } else if (warp >= 8) {
         // ================================ gather producers ==================================
+        // Thread = (pixel m of the tile, octet pair oh of the chunk).  Per stage two dependent
+        // memory round trips exist (offsets/mask/idx -> corner addresses -> corner values); the
+        // first one is taken off the critical path by fetching the NEXT stage's metadata while the
+        // current stage's corners are in flight.
         const int g_tid = threadIdx.x - 256;             // 0..255
-        const int m = g_tid & 127;                       // pixel of the tile
-        const int oh = g_tid >> 7;                       // which octet pair of the chunk: octets 2*oh, 2*oh+1
-        const long long P = (long long)p.H * p.W;
+        const int m = g_tid & 127;
+        const int oh = g_tid >> 7;
+        const int P = p.H * p.W;
+        struct Meta { float off_h, off_w, mr; int v; };
         int stage = 0, phase = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             int b, t0, nt, slice;
             decode(item, b, t0, nt, slice);
             const float *xb = d.x + (long long)b * d.xs_b;
             const float *omb = d.om + (long long)b * 3 * d.dg * 9 * P;
-            for (int kc = 0; kc < p.nkc; ++kc) {
-                for (int t = 0; t < nt; ++t) {
-                    const int tt = t0 + t;
-                    const int y = (tt / p.tiles_x) * T_R + m / T_C, xx = (tt % p.tiles_x) * T_C + m % T_C;
-                    const bool inside = y < p.H && xx < p.W;
-                    const long long pp = (long long)y * p.W + xx;
-                    uint4 h_out[2], l_out[2];
-                    int last_pair = -1;
-                    int o0 = 0, o1 = 0, o2 = 0, o3 = 0;
-                    float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f, mk = 0.f;
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const int ko = kc * KOCT + oh * 2 + u;          // global K octet
-                        __align__(16) __half h8[8];
-                        __align__(16) __half l8[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) { h8[j] = __float2half_rn(0.f); l8[j] = h8[j]; }
-                        if (inside && ko < d.n_ko) {
-                            const int pair = ko / d.opp, oc = ko % d.opp;
-                            if (pair != last_pair) {
-                                last_pair = pair;
-                                const int g = pair / 9, tap = pair % 9;
-                                const int ki = tap / 3, kj = tap % 3;
-                                const int jj = g * 9 + tap;
-                                float off_h = omb[(long long)(2 * jj) * P + pp];
-                                float off_w = omb[(long long)(2 * jj + 1) * P + pp];
-                                const float mr = omb[(long long)(2 * d.dg * 9 + jj) * P + pp];
-                                float px = 0.f, py = 0.f;
-                                if (d.pre) {
-                                    const float *pq = d.pre + (((long long)b * 9 + tap) * P + pp) * 2;
-                                    px = pq[0];
-                                    py = pq[1];
-                                } else if (d.idx) {
-                                    const int sc = d.pre_scale;
-                                    const int ys = y - sc * ki, xs = xx - sc * kj;
-                                    if (ys >= 0 && xs >= 0) {
-                                        const int yy = ys / sc, xg = xs / sc;
-                                        if (yy < d.gh && xg < d.gw) {
-                                            const long long v = d.idx[((long long)b * d.gh + yy) * d.gw + xg];
-                                            px = (float)(sc * ((int)(v % d.ref_gw) - xg));
-                                            py = (float)(sc * ((int)(v / d.ref_gw) - yy));
-                                        }
-                                    }
-                                }
-                                off_h += py;
-                                off_w += px;
-                                const float h_im = (float)(y - 1 + ki) + off_h;
-                                const float w_im = (float)(xx - 1 + kj) + off_w;
-                                w0 = w1 = w2 = w3 = 0.f;
-                                o0 = o1 = o2 = o3 = 0;
-                                mk = 0.f;
-                                if (h_im > -1.f && w_im > -1.f && h_im < (float)p.H && w_im < (float)p.W) {
-                                    const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
-                                    const int h_high = h_low + 1, w_high = w_low + 1;
-                                    const float lh = h_im - h_low, lw = w_im - w_low;
-                                    const float hh = 1.f - lh, hw = 1.f - lw;
-                                    const bool tv = h_low >= 0, bv = h_high <= p.H - 1, lv = w_low >= 0, rv = w_high <= p.W - 1;
-                                    if (tv && lv) { o0 = (int)(h_low * d.xs_y + w_low * d.xs_x); w0 = hh * hw; }
-                                    if (tv && rv) { o1 = (int)(h_low * d.xs_y + w_high * d.xs_x); w1 = hh * lw; }
-                                    if (bv && lv) { o2 = (int)(h_high * d.xs_y + w_low * d.xs_x); w2 = lh * hw; }
-                                    if (bv && rv) { o3 = (int)(h_high * d.xs_y + w_high * d.xs_x); w3 = lh * lw; }
-                                    mk = 1.f / (1.f + expf(-mr));
-                                }
-                            }
-                            if (mk != 0.f) {
-                                const int c0 = (pair / 9) * d.cpg + oc * 8;          // first of the 8 channels (xs_c == 1)
-                                const float *xc = xb + c0;
-                                const float4 a0 = *reinterpret_cast<const float4 *>(xc + o0), a1 = *reinterpret_cast<const float4 *>(xc + o0 + 4);
-                                const float4 b0 = *reinterpret_cast<const float4 *>(xc + o1), b1 = *reinterpret_cast<const float4 *>(xc + o1 + 4);
-                                const float4 c0v = *reinterpret_cast<const float4 *>(xc + o2), c1v = *reinterpret_cast<const float4 *>(xc + o2 + 4);
-                                const float4 d0 = *reinterpret_cast<const float4 *>(xc + o3), d1 = *reinterpret_cast<const float4 *>(xc + o3 + 4);
-                                const float va[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-                                const float vb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                                const float vc[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
-                                const float vd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    const float v = (w0 * va[j] + w1 * vb[j] + w2 * vc[j] + w3 * vd[j]) * mk;
-                                    const __half hh = __float2half_rn(v);
-                                    h8[j] = hh;
-                                    l8[j] = __float2half_rn(v - __half2float(hh));
-                                }
-                            }
-                        }
-                        h_out[u] = *reinterpret_cast<const uint4 *>(h8);
-                        l_out[u] = *reinterpret_cast<const uint4 *>(l8);
+            const long long *idxb = d.idx ? d.idx + (long long)b * d.gh * d.gw : nullptr;
+            const float *preb = d.pre ? d.pre + (long long)b * 9 * P * 2 : nullptr;
+            const int n_steps = p.nkc * nt;
+
+            // metadata fetch for (step, u): raw offsets + mask logit + index-map entry
+            auto fetch = [&](int step, int u, Meta &mt, int &pair_out, bool &live) {
+                const int kc = step / nt, t = step - kc * nt;
+                const int tt = t0 + t;
+                const int y = (tt / p.tiles_x) * T_R + m / T_C, xx = (tt % p.tiles_x) * T_C + m % T_C;
+                const int ko = kc * KOCT + oh * 2 + u;
+                live = step < n_steps && y < p.H && xx < p.W && ko < d.n_ko;
+                pair_out = ko / d.opp;
+                mt.off_h = mt.off_w = mt.mr = 0.f;
+                mt.v = -1;
+                if (!live) return;
+                const int g = pair_out / 9, tap = pair_out - g * 9;
+                const int jj = g * 9 + tap, pp = y * p.W + xx;
+                mt.off_h = omb[(long long)(2 * jj) * P + pp];
+                mt.off_w = omb[(long long)(2 * jj + 1) * P + pp];
+                mt.mr = omb[(long long)(2 * d.dg * 9 + jj) * P + pp];
+                if (preb) {
+                    const float2 pq = *reinterpret_cast<const float2 *>(preb + ((long long)tap * P + pp) * 2);
+                    mt.off_w += pq.x;
+                    mt.off_h += pq.y;
+                } else if (idxb) {
+                    const int sc = d.pre_scale, ki = tap / 3, kj = tap - ki * 3;
+                    const int ys = y - sc * ki, xs = xx - sc * kj;
+                    if (ys >= 0 && xs >= 0) {
+                        const int yy = ys / sc, xg = xs / sc;
+                        if (yy < d.gh && xg < d.gw) mt.v = (int)idxb[yy * d.gw + xg];
                     }
-                    mbar_wait(&empty[stage], phase ^ 1);
-                    uint8_t *s = sA + stage * A_STAGE;
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const int oct = oh * 2 + u;
-                        *reinterpret_cast<uint4 *>(s + oct * A_OCT_B + m * 16) = h_out[u];
-                        *reinterpret_cast<uint4 *>(s + A_HALF + oct * A_OCT_B + m * 16) = l_out[u];
-                    }
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&full[stage]);
-                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                 }
+            };
+
+            Meta mt[2], nx[2];
+            int pr[2], npr[2];
+            bool lv[2], nlv[2];
+            fetch(0, 0, mt[0], pr[0], lv[0]);
+            fetch(0, 1, mt[1], pr[1], lv[1]);
+            for (int step = 0; step < n_steps; ++step) {
+                const int kc = step / nt, t = step - kc * nt;
+                const int tt = t0 + t;
+                const int y = (tt / p.tiles_x) * T_R + m / T_C, xx = (tt % p.tiles_x) * T_C + m % T_C;
+                // ---- sampling points of the two octets
+                int o[2][4];
+                float wq[2][4], mk[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    o[u][0] = o[u][1] = o[u][2] = o[u][3] = 0;
+                    wq[u][0] = wq[u][1] = wq[u][2] = wq[u][3] = 0.f;
+                    mk[u] = 0.f;
+                    if (lv[u]) {
+                        const int g = pr[u] / 9, tap = pr[u] - g * 9, ki = tap / 3, kj = tap - ki * 3;
+                        float off_h = mt[u].off_h, off_w = mt[u].off_w;
+                        if (mt[u].v >= 0) {
+                            const int sc = d.pre_scale;
+                            const int yy = (y - sc * ki) / sc, xg = (xx - sc * kj) / sc;
+                            const int vy = mt[u].v / d.ref_gw, vx = mt[u].v - vy * d.ref_gw;
+                            off_w += (float)(sc * (vx - xg));
+                            off_h += (float)(sc * (vy - yy));
+                        }
+                        const float h_im = (float)(y - 1 + ki) + off_h;
+                        const float w_im = (float)(xx - 1 + kj) + off_w;
+                        if (h_im > -1.f && w_im > -1.f && h_im < (float)p.H && w_im < (float)p.W) {
+                            const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
+                            const int h_high = h_low + 1, w_high = w_low + 1;
+                            const float lh = h_im - h_low, lw = w_im - w_low;
+                            const float hh = 1.f - lh, hw = 1.f - lw;
+                            const bool tv = h_low >= 0, bv = h_high <= p.H - 1, lvv = w_low >= 0, rv = w_high <= p.W - 1;
+                            const int cbase = g * d.cpg + (oh * 2 + u + kc * KOCT - pr[u] * d.opp) * 8;
+                            if (tv && lvv) { o[u][0] = (int)(h_low * d.xs_y + w_low * d.xs_x) + cbase; wq[u][0] = hh * hw; }
+                            if (tv && rv) { o[u][1] = (int)(h_low * d.xs_y + w_high * d.xs_x) + cbase; wq[u][1] = hh * lw; }
+                            if (bv && lvv) { o[u][2] = (int)(h_high * d.xs_y + w_low * d.xs_x) + cbase; wq[u][2] = lh * hw; }
+                            if (bv && rv) { o[u][3] = (int)(h_high * d.xs_y + w_high * d.xs_x) + cbase; wq[u][3] = lh * lw; }
+                            mk[u] = 1.f / (1.f + expf(-mt[u].mr));
+                        }
+                    }
+                }
+                // ---- corner fetches of both octets in flight together, then the next stage's metadata
+                float4 cv[2][4][2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        cv[u][c][0] = *reinterpret_cast<const float4 *>(xb + o[u][c]);
+                        cv[u][c][1] = *reinterpret_cast<const float4 *>(xb + o[u][c] + 4);
+                    }
+                fetch(step + 1, 0, nx[0], npr[0], nlv[0]);
+                fetch(step + 1, 1, nx[1], npr[1], nlv[1]);
+                // ---- blend, modulate, split
+                uint4 h_out[2], l_out[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    __align__(16) __half h8[8];
+                    __align__(16) __half l8[8];
+#pragma unroll
+                    for (int hh2 = 0; hh2 < 2; ++hh2) {
+                        const float a4[4] = {cv[u][0][hh2].x, cv[u][0][hh2].y, cv[u][0][hh2].z, cv[u][0][hh2].w};
+                        const float b4[4] = {cv[u][1][hh2].x, cv[u][1][hh2].y, cv[u][1][hh2].z, cv[u][1][hh2].w};
+                        const float c4[4] = {cv[u][2][hh2].x, cv[u][2][hh2].y, cv[u][2][hh2].z, cv[u][2][hh2].w};
+                        const float d4[4] = {cv[u][3][hh2].x, cv[u][3][hh2].y, cv[u][3][hh2].z, cv[u][3][hh2].w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float v = (wq[u][0] * a4[j] + wq[u][1] * b4[j] + wq[u][2] * c4[j] + wq[u][3] * d4[j]) * mk[u];
+                            const __half hq = __float2half_rn(v);
+                            h8[hh2 * 4 + j] = hq;
+                            l8[hh2 * 4 + j] = __float2half_rn(v - __half2float(hq));
+                        }
+                    }
+                    h_out[u] = *reinterpret_cast<const uint4 *>(h8);
+                    l_out[u] = *reinterpret_cast<const uint4 *>(l8);
+                }
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t *sdst = sA + stage * A_STAGE;
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int oct = oh * 2 + u;
+                    *reinterpret_cast<uint4 *>(sdst + oct * A_OCT_B + m * 16) = h_out[u];
+                    *reinterpret_cast<uint4 *>(sdst + A_HALF + oct * A_OCT_B + m * 16) = l_out[u];
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[stage]);
+                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) { mt[u] = nx[u]; pr[u] = npr[u]; lv[u] = nlv[u]; }
             }
         }
     }
