@@ -47,7 +47,7 @@ constexpr int W_HDR = 256;                // packed-weight blob header bytes
 // any Cin/Cout fits; 64->64 degenerates to 2 chunks per item.  Activation stages stream
 // through a 3-deep TMA ring exactly as in the correlation kernel.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
                     const __grid_constant__ CUtensorMap tm2_hi, const __grid_constant__ CUtensorMap tm2_lo,
                     const ConvPtrs q, const ConvParams p) {
@@ -79,7 +79,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < NSTAGE; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < NBST; ++i) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], 1); }
-        for (int i = 0; i < MAXT; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        for (int i = 0; i < MAXT; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -188,28 +188,38 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
         }
     } else if (warp >= 4) {
         // ================================ epilogue ==========================================
-        const int e = threadIdx.x - 128;
+        // 8 warps: warp w owns TMEM lane quarter (w & 3) = 32 output pixels, and the 32-column block
+        // c0 = 32 * ((w - 4) >> 2) of every accumulator.  (With 4 warps the serial per-thread chain
+        // TMEM load -> scale/act -> fp16 split -> store of 64 channels took longer than the tile's MMAs.)
+        const int e = (threadIdx.x - 128) & 127;            // pixel of the tile
         const int quarter = warp & 3;
+        const int c0 = ((warp - 4) >> 2) * 32;
         const float out_scale = ldexpf(1.f, -(p.sa_in + sw));
         const float res_scale = ldexpf(1.f, -p.sa_res);
         const float so = ldexpf(1.f, p.sa_out);
+        const bool has1 = q.res_hi != nullptr;              // warp-uniform
         uint32_t tph = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             int b, t0, nt, slice;
             decode(item, b, t0, nt, slice);
             const int o_base = slice * p.N;
-            asm volatile("bar.sync 1, 128;" ::: "memory");          // previous item's sbias readers are done
-            if (e < p.N) sbias[e] = (q.bias && o_base + e < p.Cout) ? q.bias[o_base + e] : 0.f;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");          // previous item's sbias readers are done
+            if (threadIdx.x - 128 < p.N) sbias[threadIdx.x - 128] =
+                (q.bias && o_base + (int)threadIdx.x - 128 < p.Cout) ? q.bias[o_base + threadIdx.x - 128] : 0.f;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             for (int t = 0; t < nt; ++t) {
                 const int tt = t0 + t;
                 const int y = (tt / p.tiles_x) * T_R + e / T_C, x = (tt % p.tiles_x) * T_C + e % T_C;
                 const bool ok = y < p.H && x < p.W;
+                ResRegs ra;
+                if (has1 && c0 < p.N) prefetch_residual(q.res_hi, q.res_lo, p, b, y, x, ok, o_base, c0, ra);
                 mbar_wait(&tfull[t], (tph >> t) & 1u);
                 tph ^= 1u << t;
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + t * 2 * p.N;
-                epilogue_store_tile(q, p, taddr, b, y, x, ok, o_base, sbias, out_scale, res_scale, so);
+                if (c0 < p.N)
+                    epilogue_store_block(q, p, taddr, c0, b, y, x, ok, o_base, sbias, out_scale, res_scale, so,
+                                         has1 ? &ra : nullptr);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[t]);
@@ -469,7 +479,7 @@ extern "C" int c2m_conv3x3(const c2m_conv3x3_args *a, c2m_stream_t stream) {
     C2M_CUDA(cudaGetDevice(&dev));
     C2M_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int n_items = a->B * p.n_st * p.nslice;
-    conv3x3_umma_kernel<<<n_items < sms ? n_items : sms, 256, smem, st>>>(mh, ml, m2h, m2l, q, p);
+    conv3x3_umma_kernel<<<n_items < sms ? n_items : sms, 384, smem, st>>>(mh, ml, m2h, m2l, q, p);
     C2M_LAUNCH_CHECK("conv3x3_umma_kernel");
     return C2M_OK;
 }

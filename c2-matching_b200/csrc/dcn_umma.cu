@@ -179,7 +179,8 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
                 tph ^= 1u << t;
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + t * p.N;
-                epilogue_store_tile(q, p, taddr, b, y, x, ok, o_base, sbias, out_scale, res_scale, so);
+                for (int c0 = 0; c0 < p.N; c0 += 32)
+                    epilogue_store_block(q, p, taddr, c0, b, y, x, ok, o_base, sbias, out_scale, res_scale, so);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[t]);

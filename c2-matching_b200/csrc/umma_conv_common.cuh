@@ -32,10 +32,36 @@ struct ConvPtrs {
 
 // One thread = one output pixel (TMEM lane); `taddr` already carries the lane quarter and the
 // accumulator's first column.
-__device__ __forceinline__ void epilogue_store_tile(const ConvPtrs &q, const ConvParams &p, uint32_t taddr, int b, int y,
-                                                    int x, bool ok, int o_base, const float *sbias, float out_scale,
-                                                    float res_scale, float so) {
-                    for (int c0 = 0; c0 < p.N; c0 += 32) {
+// Residual registers of one 32-column block (4 channel octets); fetched by `prefetch_residual`
+// BEFORE the thread blocks on the accumulator / tcgen05.ld, so the HBM/L2 latency of the residual
+// overlaps the MMAs instead of being paid once per octet inside the loop.
+struct ResRegs {
+    uint4 h[4], l[4];
+};
+
+__device__ __forceinline__ void prefetch_residual(const __half *rh, const __half *rl, const ConvParams &p, int b, int y,
+                                                  int x, bool ok, int o_base, int c0, ResRegs &r) {
+#pragma unroll
+    for (int o8 = 0; o8 < 4; ++o8) {
+        const int oct = (o_base + c0) / 8 + o8;
+        if (ok && c0 + o8 * 8 < p.N && oct < p.C8out) {
+            const size_t off = ((((size_t)b * p.C8out + oct) * p.H + y) * p.W + x) * 8;
+            r.h[o8] = *reinterpret_cast<const uint4 *>(rh + off);
+            r.l[o8] = *reinterpret_cast<const uint4 *>(rl + off);
+        } else {
+            r.h[o8] = make_uint4(0, 0, 0, 0);
+            r.l[o8] = make_uint4(0, 0, 0, 0);
+        }
+    }
+}
+
+// One 32-column block [c0, c0+32) of the accumulator.  r1: prefetched first residual (or null);
+// a second residual (q.res2_*, rare) is read in place.
+__device__ __forceinline__ void epilogue_store_block(const ConvPtrs &q, const ConvParams &p, uint32_t taddr, int c0, int b,
+                                                     int y, int x, bool ok, int o_base, const float *sbias,
+                                                     float out_scale, float res_scale, float so,
+                                                     const ResRegs *r1 = nullptr) {
+                    {
                         uint32_t reg[32];
                         if (p.N - c0 >= 32) {
                             tmem_ld_32x32(taddr + c0, reg);
@@ -72,7 +98,7 @@ __device__ __forceinline__ void epilogue_store_tile(const ConvPtrs &q, const Con
                         } else {
                             tmem_ld_wait();
                         }
-                        if (!ok) continue;
+                        if (!ok) return;
                         const int ncol = min(32, p.N - c0);
                         float v[32];
     #pragma unroll
@@ -99,11 +125,9 @@ __device__ __forceinline__ void epilogue_store_tile(const ConvPtrs &q, const Con
                                 if (o8 * 8 >= ncol || oct >= p.C8out) break;
                                 const size_t off = ((((size_t)b * p.C8out + oct) * p.H + y) * p.W + x) * 8;
                                 float r8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                                if (q.res_hi) {
-                                    const uint4 rh = *reinterpret_cast<const uint4 *>(q.res_hi + off);
-                                    const uint4 rl = *reinterpret_cast<const uint4 *>(q.res_lo + off);
-                                    const __half *hh = reinterpret_cast<const __half *>(&rh);
-                                    const __half *ll = reinterpret_cast<const __half *>(&rl);
+                                if (r1) {
+                                    const __half *hh = reinterpret_cast<const __half *>(&r1->h[o8]);
+                                    const __half *ll = reinterpret_cast<const __half *>(&r1->l[o8]);
     #pragma unroll
                                     for (int j = 0; j < 8; ++j) r8[j] = (__half2float(hh[j]) + __half2float(ll[j])) * res_scale;
                                 }
