@@ -193,11 +193,12 @@ def run_ours(args, rank, world, local_rank):
     if sampler:
         sampler.start()
     ops.profile_enable(True)
-    ops.profile_corr_search_ms()
+    for k in ops.PROF_KERNELS:
+        ops.profile_collect(k)
     n0 = c2m.launch_count()
     ms_dev = timed(step_dev, args.steps)
     launches = c2m.launch_count() - n0
-    search_ms, search_n = ops.profile_corr_search_ms()
+    prof = {k: ops.profile_collect(k) for k in ops.PROF_KERNELS}
     ops.profile_enable(False)
     clocks = sampler.stop() if sampler else None
     ms_e2e = timed(step_e2e, args.steps)
@@ -216,22 +217,36 @@ def run_ours(args, rank, world, local_rank):
         peak_src = 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)'
         if not peak:
             peak, peak_src = 1400.0, 'fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained)'
-        flops, byts = corr_algorithmic(BATCH)
-        per_launch_s = search_ms / max(search_n, 1) / 1e3
-        achieved = flops / per_launch_s / 1e12
+        # per kernel class: device time inside the timed steps (CUDA events on the launching stream,
+        # recorded by the library), algorithmic flops / bytes per SURVEY.md §8(d)
+        classes = {}
+        for k, r in prof.items():
+            if r['launches']:
+                classes[k] = {'ms_per_step': r['ms'] / args.steps, 'launches_per_step': r['launches'] / args.steps,
+                              'share_of_step': r['ms'] / ms_dev if world == 1 else None,
+                              'algorithmic_tflops': r['flops'] / (r['ms'] / 1e3) / 1e12,
+                              'algorithmic_gbps': r['bytes'] / (r['ms'] / 1e3) / 1e9}
+        dom = max(prof, key=lambda k: prof[k]['ms'])
+        r = prof[dom]
+        name = {'corr_search': 'corr_umma_kernel', 'conv3x3': 'conv3x3_umma_kernel', 'dcn': 'dcn_umma_kernel'}[dom]
+        achieved = r['flops'] / (r['ms'] / 1e3) / 1e12
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'corr_umma_traffic.json'))).get('dram_bytes_per_launch')
+            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'dominant_kernel_traffic.json'))).get(name)
         except Exception:
             pass
-        roofline = {'bound': 'tensor', 'kernel': 'corr_umma_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
+        issued = {'conv3x3': 4.0, 'corr_search': 3.0, 'dcn': 3.0}[dom]
+        roofline = {'bound': 'tensor', 'kernel': name, 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
                     'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
-                    'ms_per_launch': per_launch_s * 1e3, 'algorithmic_flops_per_launch': flops,
-                    'algorithmic_bytes_per_launch': byts,
-                    'issued_mma_flops_per_launch': 3 * flops * (160 * 160 / (158. * 158.)) ** 2,
-                    'hbm_gbps_at_algorithmic_bytes': byts / per_launch_s / 1e9,
-                    'note': '3 fp16 MMAs per K step (hi*hi+hi*lo+lo*hi) for fp32-grade scores: tensor-pipe busy '
-                            'fraction is ~3x the algorithmic fraction'}
+                    'ms_per_launch': r['ms'] / r['launches'], 'launches_timed': r['launches'],
+                    'algorithmic_flops_per_launch': r['flops'] / r['launches'],
+                    'algorithmic_bytes_per_launch': r['bytes'] / r['launches'],
+                    'hbm_gbps_at_algorithmic_bytes': r['bytes'] / (r['ms'] / 1e3) / 1e9,
+                    'issued_over_algorithmic_mma': issued,
+                    'note': 'fp32-grade results from fp16 tensor cores: every product is issued as split hi/lo '
+                            'partial products (x3 for the correlation / DCN, x4 for the stacked-B convolution), so the '
+                            'tensor-pipe busy fraction is `issued_over_algorithmic_mma` x `frac`',
+                    'per_kernel_class': classes}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cpu = cpu_baseline(1)

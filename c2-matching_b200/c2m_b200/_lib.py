@@ -64,7 +64,8 @@ SYMBOLS = {
     'c2m_dcn_tc_pack_weights_f32': (ctypes.c_int, [c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     'c2m_dcn_v2_fused_tc': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     'c2m_profile_enable': (ctypes.c_int, [ctypes.c_int]),
-    'c2m_profile_corr_search_ms': (ctypes.c_int, [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)]),
+    'c2m_profile_collect': (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int),
+                                           ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
     'c2m_corr_workspace_bytes': (ctypes.c_size_t, [ctypes.c_int] * 9),
     'c2m_corr_argmax_f32': (ctypes.c_int, [c_f32p, c_f32p] + [ctypes.c_int] * 12 + [ctypes.c_uint, c_i64p, c_f32p,
                                                                                  ctypes.c_void_p, ctypes.c_size_t,

@@ -31,12 +31,16 @@ def profile_enable(on=True):
     _lib.check(_lib.lib().c2m_profile_enable(int(bool(on))), 'c2m_profile_enable')
 
 
-def profile_corr_search_ms():
-    """(total device ms, launches) of the correlation search kernel since the last query."""
+PROF_KERNELS = {'corr_search': 0, 'conv3x3': 1, 'dcn': 2}
+
+
+def profile_collect(kernel):
+    """{'ms', 'launches', 'flops', 'bytes'} of one kernel class since the last collect."""
     import ctypes
-    ms, n = ctypes.c_float(0), ctypes.c_int(0)
-    _lib.check(_lib.lib().c2m_profile_corr_search_ms(ctypes.byref(ms), ctypes.byref(n)), 'c2m_profile_corr_search_ms')
-    return float(ms.value), int(n.value)
+    ms, n, fl, by = ctypes.c_float(0), ctypes.c_int(0), ctypes.c_double(0), ctypes.c_double(0)
+    _lib.check(_lib.lib().c2m_profile_collect(PROF_KERNELS[kernel], ctypes.byref(ms), ctypes.byref(n),
+                                              ctypes.byref(fl), ctypes.byref(by)), 'c2m_profile_collect')
+    return {'ms': float(ms.value), 'launches': int(n.value), 'flops': float(fl.value), 'bytes': float(by.value)}
 
 
 def _workspace(nbytes, device):

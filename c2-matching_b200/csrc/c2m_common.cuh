@@ -15,6 +15,13 @@ namespace c2m {
 void set_error(const char *fmt, ...);
 void count_launch(unsigned n = 1);
 
+// Measurement hook (include/c2m_sm100.h c2m_profile_*): kernel classes timed with CUDA events on the
+// launching stream while profiling is enabled.
+enum ProfKernel { PROF_CORR_SEARCH = 0, PROF_CONV3X3 = 1, PROF_DCN = 2, PROF_NKERNELS = 3 };
+bool prof_enabled();
+void *prof_begin(int kernel, double flops, double bytes, cudaStream_t st);   // null when disabled
+void prof_end(void *handle, cudaStream_t st);
+
 #define C2M_CHECK_ARG(cond, ...)                 \
     do {                                         \
         if (!(cond)) {                           \

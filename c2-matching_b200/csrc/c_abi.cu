@@ -23,7 +23,29 @@ void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxe
 
 static std::atomic<int> g_profile{0};
 static std::mutex g_prof_mu;
-static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+struct ProfRec { int kernel; double flops, bytes; cudaEvent_t e0, e1; };
+static std::vector<ProfRec *> g_prof_recs;
+
+bool prof_enabled() { return g_profile.load() != 0; }
+
+void *prof_begin(int kernel, double flops, double bytes, cudaStream_t st) {
+    if (!prof_enabled()) return nullptr;
+    ProfRec *r = new ProfRec{kernel, flops, bytes, nullptr, nullptr};
+    if (cudaEventCreate(&r->e0) != cudaSuccess || cudaEventCreate(&r->e1) != cudaSuccess ||
+        cudaEventRecord(r->e0, st) != cudaSuccess) {
+        delete r;
+        return nullptr;
+    }
+    return r;
+}
+
+void prof_end(void *handle, cudaStream_t st) {
+    if (!handle) return;
+    ProfRec *r = static_cast<ProfRec *>(handle);
+    cudaEventRecord(r->e1, st);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_recs.push_back(r);
+}
 
 static int make_geom(CorrGeom &g, int B, int C, int h, int w, int hr, int wr, int patch, int s_in, int s_ref) {
     C2M_CHECK_ARG(B > 0 && C > 0, "corr: empty batch or channels (B=%d C=%d)", B, C);
@@ -118,20 +140,12 @@ extern "C" int c2m_corr_argmax_f32(const float *fin, const float *fref, int B, i
     if ((rc = corr_prep_launch(fin, B, C, g.Cp, h * w, l2norm, 0, ws, ws.p32_in, ws.hi_in, ws.lo_in, ws.ss_in, st))) return rc;
     if ((rc = corr_prep_launch(fref, B, C, g.Cp, hr * wr, l2norm, 1, ws, ws.p32_ref, ws.hi_ref, ws.lo_ref, ws.ss_ref, st))) return rc;
     if ((rc = corr_rinv_launch(g, ws, is_norm, st))) return rc;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    const bool prof = g_profile.load() != 0;
-    if (prof) {
-        C2M_CUDA(cudaEventCreate(&e0));
-        C2M_CUDA(cudaEventCreate(&e1));
-        C2M_CUDA(cudaEventRecord(e0, st));
-    }
+    const double flops = 2.0 * g.C * g.patch * g.patch * (double)g.NQ * g.NR * g.B;
+    const double bytes = (4.0 * g.C * ((double)g.h * g.w + (double)g.hr * g.wr) + 12.0 * g.NQ) * g.B;
+    void *ph = prof_begin(PROF_CORR_SEARCH, flops, bytes, st);
     rc = use_umma ? corr_search_umma_launch(g, ws, st) : corr_search_generic_launch(g, ws, st);
     if (rc) return rc;
-    if (prof) {
-        C2M_CUDA(cudaEventRecord(e1, st));
-        std::lock_guard<std::mutex> lk(g_prof_mu);
-        g_prof_events.emplace_back(e0, e1);
-    }
+    prof_end(ph, st);
     return corr_rescore_launch(g, ws, is_norm, norm_input, idx, val, st);
 }
 
@@ -140,22 +154,24 @@ extern "C" int c2m_profile_enable(int on) {
     return C2M_OK;
 }
 
-extern "C" int c2m_profile_corr_search_ms(float *ms_total, int *launches) {
-    C2M_CHECK_ARG(ms_total && launches, "profile: null pointer");
+extern "C" int c2m_profile_collect(int kernel, float *ms_total, int *launches, double *flops, double *bytes) {
+    C2M_CHECK_ARG(ms_total && launches && flops && bytes && kernel >= 0 && kernel < PROF_NKERNELS, "profile_collect: bad argument");
     std::lock_guard<std::mutex> lk(g_prof_mu);
     float total = 0.f;
     int n = 0;
-    for (auto &pr : g_prof_events) {
-        C2M_CUDA(cudaEventSynchronize(pr.second));
+    double fl = 0.0, by = 0.0;
+    std::vector<ProfRec *> keep;
+    for (ProfRec *r : g_prof_recs) {
+        if (r->kernel != kernel) { keep.push_back(r); continue; }
+        C2M_CUDA(cudaEventSynchronize(r->e1));
         float ms = 0.f;
-        C2M_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
-        total += ms;
-        ++n;
-        cudaEventDestroy(pr.first);
-        cudaEventDestroy(pr.second);
+        C2M_CUDA(cudaEventElapsedTime(&ms, r->e0, r->e1));
+        total += ms; fl += r->flops; by += r->bytes; ++n;
+        cudaEventDestroy(r->e0);
+        cudaEventDestroy(r->e1);
+        delete r;
     }
-    g_prof_events.clear();
-    *ms_total = total;
-    *launches = n;
+    g_prof_recs.swap(keep);
+    *ms_total = total; *launches = n; *flops = fl; *bytes = by;
     return C2M_OK;
 }

@@ -479,7 +479,14 @@ extern "C" int c2m_conv3x3(const c2m_conv3x3_args *a, c2m_stream_t stream) {
     C2M_CUDA(cudaGetDevice(&dev));
     C2M_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int n_items = a->B * p.n_st * p.nslice;
+    // algorithmic work: 2*Cin*Cout*9 flops per output pixel; bytes = PSA in (4 B/elem) + out
+    const double cin_t = (double)a->Cin + a->Cin2, px = (double)a->B * a->H * a->W;
+    const double flops = 2.0 * cin_t * a->Cout * 9.0 * px;
+    const double bytes = 4.0 * px * (cin_t + a->Cout * ((a->out_hi ? 1 : 0) + (a->out_f32 ? 1 : 0)) +
+                                     a->Cout * ((a->res_hi ? 1 : 0) + (a->res2_hi ? 1 : 0) + (a->add_f32 ? 1 : 0)));
+    void *ph = prof_begin(PROF_CONV3X3, flops, bytes, st);
     conv3x3_umma_kernel<<<n_items < sms ? n_items : sms, 384, smem, st>>>(mh, ml, m2h, m2l, q, p);
     C2M_LAUNCH_CHECK("conv3x3_umma_kernel");
+    prof_end(ph, st);
     return C2M_OK;
 }

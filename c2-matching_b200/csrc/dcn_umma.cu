@@ -461,7 +461,13 @@ extern "C" int c2m_dcn_v2_fused_tc(const c2m_dcn_tc_args *a, c2m_stream_t stream
     C2M_CUDA(cudaGetDevice(&dev));
     C2M_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int n_items = a->B * p.n_st * p.nslice;
+    // flops = 2*B*Cout*C*9*Ho*Wo; bytes = 4*B*(C*H*W + 3*dg*9*H*W + Cout*H*W) + weights
+    const double px = (double)a->B * a->H * a->W;
+    const double flops = 2.0 * a->Cout * a->C * 9.0 * px;
+    const double bytes = 4.0 * px * (a->C + 27.0 * a->dg + a->Cout) + 4.0 * a->Cout * (a->C * 9.0 + 1.0);
+    void *ph = prof_begin(PROF_DCN, flops, bytes, st);
     dcn_umma_kernel<<<n_items < sms ? n_items : sms, 512, smem, st>>>(q, p, d);
     C2M_LAUNCH_CHECK("dcn_umma_kernel");
+    prof_end(ph, st);
     return C2M_OK;
 }

@@ -166,12 +166,13 @@ int c2m_dcn_v2_fused_tc(const c2m_dcn_tc_args *args, c2m_stream_t stream);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 unsigned long long c2m_launch_count(void);
 
-/* Measurement hook (bench.py `roofline`): while enabled, every c2m_corr_argmax_f32 call brackets
- * its candidate-search kernel (the dominant kernel of the path) with CUDA events on the caller's
- * stream.  c2m_profile_corr_search_ms synchronises those events, returns the summed device time
- * in *ms_total and the number of search launches in *launches, and clears the list. */
+/* Measurement hook (bench.py `roofline`): while enabled, the library brackets every launch of its
+ * three heavy kernel classes with CUDA events on the caller's stream:
+ *   0 = correlation candidate search (corr_umma / generic), 1 = conv3x3_umma, 2 = dcn_umma.
+ * c2m_profile_collect synchronises the recorded events of one class, returns their summed device
+ * time, launch count and summed ALGORITHMIC flops / bytes (SURVEY.md §8d formulas), and clears them. */
 int c2m_profile_enable(int on);
-int c2m_profile_corr_search_ms(float *ms_total, int *launches);
+int c2m_profile_collect(int kernel, float *ms_total, int *launches, double *flops, double *bytes);
 
 #ifdef __cplusplus
 }
