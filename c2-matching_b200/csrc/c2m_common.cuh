@@ -166,6 +166,12 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo,
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
            (1ull << 46);
 }
+// Same descriptor advanced by `byte_off` (multiple of 16; the 14-bit start-address field cannot
+// carry: shared memory is < 2^18 bytes) — one 32-bit add on the low word.
+__device__ __forceinline__ uint64_t umma_desc_advance(uint64_t desc, uint32_t byte_off) {
+    const uint32_t lo = (uint32_t)desc + (byte_off >> 4);
+    return (desc & 0xFFFFFFFF00000000ull) | lo;
+}
 // Instruction descriptor for kind::f16: D fp32, A/B fp16 (0) or bf16 (1), both K-major.
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, int ab_fmt) {
     return (1u << 4) | ((uint32_t)ab_fmt << 7) | ((uint32_t)ab_fmt << 10) | ((uint32_t)(N >> 3) << 17) |

@@ -142,8 +142,9 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
         if (lane == 0) {
             // B = [W_hi | W_lo] stacked along N (2N rows per octet): an N = 64 MMA occupies the tensor
             // pipe as long as an N = 128 one (A-operand fetch bound, ncu: pipe_tc 81 % vs math 40 %),
-            // so x_hi*[W_hi|W_lo] + x_lo*[W_hi|W_lo] is 2 MMAs per K step instead of 3 (and exact)
+            // so x_hi*[W_hi|W_lo] (N = 2N) + x_lo*W_hi (N) is 2 MMAs per K step instead of 3
             const uint32_t idesc = umma_idesc_f16(128, 2 * p.N, 0);
+            const uint32_t idesc_lo = umma_idesc_f16(128, p.N, 0);
             const uint32_t b_lbo = 2 * p.N * 16;             // next channel octet of the weights
             int stage = 0, phase = 0, bst = 0, bphase = 0;
             uint32_t tph = 0;                                  // per-accumulator phase bits
@@ -162,19 +163,21 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                         const uint32_t d = tmem_base + t * 2 * p.N;
                         mbar_wait(&full[stage], phase);
                         tc_fence_after();
-                        const uint32_t a_hi = smem_u32(sA + stage * A_STAGE), a_lo = a_hi + A_HALF;
+                        const uint32_t a_hi = smem_u32(sA + stage * A_STAGE);
+                        // descriptors of (tap 0, k-step 0); every other MMA is a constant offset away
+                        const uint64_t dah0 = umma_smem_desc(a_hi, A_OCT_B, ROW_B);
+                        const uint64_t dal0 = umma_smem_desc(a_hi + A_HALF, A_OCT_B, ROW_B);
+                        const uint64_t db0 = umma_smem_desc(w_st, b_lbo, 128);
 #pragma unroll
                         for (int tap = 0; tap < 9; ++tap) {
-                            const uint32_t toff = ((tap / 3) * A_C + tap % 3) * 16;
-                            const uint32_t wtap = (tap * KOCT) * b_lbo;
 #pragma unroll
                             for (int j = 0; j < KOCT / 2; ++j) {
-                                const uint32_t ao = toff + j * 2 * A_OCT_B, bo = wtap + j * 2 * b_lbo;
-                                const uint64_t dah = umma_smem_desc(a_hi + ao, A_OCT_B, ROW_B);
-                                const uint64_t dal = umma_smem_desc(a_lo + ao, A_OCT_B, ROW_B);
-                                const uint64_t db = umma_smem_desc(w_st + bo, b_lbo, 128);
-                                umma_f16(d, dah, db, idesc, (kc | tap | j) != 0);
-                                umma_f16(d, dal, db, idesc, 1);
+                                const uint32_t ao = ((tap / 3) * A_C + tap % 3) * 16 + j * 2 * A_OCT_B;
+                                const uint32_t bo = (tap * KOCT + j * 2) * b_lbo;
+                                const uint64_t db = umma_desc_advance(db0, bo);
+                                // x_hi * [W_hi | W_lo]  (N = 2N)  +  x_lo * W_hi  (first N rows only)
+                                umma_f16(d, umma_desc_advance(dah0, ao), db, idesc, (kc | tap | j) != 0);
+                                umma_f16(d, umma_desc_advance(dal0, ao), db, idesc_lo, 1);
                             }
                         }
                         umma_commit(&empty[stage]);
