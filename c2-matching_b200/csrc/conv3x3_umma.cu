@@ -19,6 +19,8 @@
 // on weights.  Epilogue (4 warps, one output pixel per thread): *2^-(sa+sw) + bias, ReLU /
 // LeakyReLU, optional residual add (a second PSA tensor), re-split to hi/lo and store — the
 // output is directly the next convolution's operand, no fp32 round trip through HBM.
+#include <cstdlib>
+
 #include "umma_conv_common.cuh"
 
 namespace c2m {
@@ -103,9 +105,35 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
     };
 
     if (warp == 0) {
-        // ================================ producer ==========================================
+        // ================================ activation producer ===============================
         if (lane == 0) {
-            int stage = 0, phase = 0, bst = 0, bphase = 0;
+            int stage = 0, phase = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                int b, t0, nt, slice;
+                decode(item, b, t0, nt, slice);
+                for (int kc = 0; kc < p.nkc; ++kc) {
+                    const bool first = kc < p.nkc_a;
+                    const CUtensorMap *mh = first ? &tm_hi : &tm2_hi, *ml = first ? &tm_lo : &tm2_lo;
+                    const int oct0 = (first ? kc : kc - p.nkc_a) * KOCT;
+                    for (int t = 0; t < nt; ++t) {
+                        const int tt = t0 + t;
+                        const int y0 = (tt / p.tiles_x) * T_R, x0 = (tt % p.tiles_x) * T_C;
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        uint8_t *s = sA + stage * A_STAGE;
+                        mbar_arrive_expect_tx(&full[stage], A_STAGE);
+                        tma_load_4d(s, mh, &full[stage], (x0 - 1) * 8, y0 - 1, oct0, b);
+                        tma_load_4d(s + A_HALF, ml, &full[stage], (x0 - 1) * 8, y0 - 1, oct0, b);
+                        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ================================ weight producer ===================================
+        // its own thread: a chunk is requested the moment its slot frees, not after the
+        // activation stream of the previous chunk has been issued
+        if (lane == 0) {
+            int bst = 0, bphase = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 int b, t0, nt, slice;
                 decode(item, b, t0, nt, slice);
@@ -121,19 +149,6 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                             : "memory");
                     }
                     if (++bst == NBST) { bst = 0; bphase ^= 1; }
-                    const bool first = kc < p.nkc_a;
-                    const CUtensorMap *mh = first ? &tm_hi : &tm2_hi, *ml = first ? &tm_lo : &tm2_lo;
-                    const int oct0 = (first ? kc : kc - p.nkc_a) * KOCT;
-                    for (int t = 0; t < nt; ++t) {
-                        const int tt = t0 + t;
-                        const int y0 = (tt / p.tiles_x) * T_R, x0 = (tt % p.tiles_x) * T_C;
-                        mbar_wait(&empty[stage], phase ^ 1);
-                        uint8_t *s = sA + stage * A_STAGE;
-                        mbar_arrive_expect_tx(&full[stage], A_STAGE);
-                        tma_load_4d(s, mh, &full[stage], (x0 - 1) * 8, y0 - 1, oct0, b);
-                        tma_load_4d(s + A_HALF, ml, &full[stage], (x0 - 1) * 8, y0 - 1, oct0, b);
-                        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-                    }
                 }
             }
         }
@@ -450,6 +465,12 @@ extern "C" int c2m_conv3x3(const c2m_conv3x3_args *a, c2m_stream_t stream) {
     p.Cout = a->Cout; p.N = slice_n(a->Cout); p.nslice = n_slice(a->Cout);
     p.tiles_x = ceil_div(a->W, T_C); p.tiles_y = ceil_div(a->H, T_R);
     p.T = 512 / (2 * p.N) < MAXT ? 512 / (2 * p.N) : MAXT;
+    // small problems (e.g. 64->64 on 160x160 maps = 200 items of 4 tiles for 148 SMs): halve the item size
+    if (p.T > 2 && (long long)a->B * p.tiles_x * p.tiles_y * p.nslice / p.T < 3 * 148) p.T = 2;
+    if (const char *ev = getenv("C2M_CONV_T")) {          // tuning knob: tiles per work item
+        const int t = atoi(ev);
+        if (t >= 1 && t < p.T) p.T = t;
+    }
     p.stacked = 1;
     p.n_st = ceil_div(p.tiles_x * p.tiles_y, p.T);
     p.act = a->act; p.sa_in = a->sa_in; p.sa_res = a->sa_res; p.sa_out = a->sa_out;
