@@ -48,6 +48,17 @@ def install_reference_shims():
 
     mmcv.scandir = scandir
     mmcv.mkdir_or_exist = lambda p, mode=0o777: os.makedirs(p, mode=mode, exist_ok=True)
+    # image helpers with mmcv 0.4.x semantics (only needed by the dataset fixture)
+    import cv2
+    mmcv.imfrombytes = lambda content, flag='color': cv2.imdecode(np.frombuffer(content, np.uint8), cv2.IMREAD_COLOR)
+    mmcv.bgr2rgb = lambda img: cv2.cvtColor(img, cv2.COLOR_BGR2RGB)
+
+    def impad(img, shape, pad_val=0):
+        out = np.full(tuple(shape) + img.shape[2:], pad_val, dtype=img.dtype)
+        out[:img.shape[0], :img.shape[1], ...] = img
+        return out
+
+    mmcv.impad = impad
     runner = types.ModuleType('mmcv.runner')
     runner.master_only = lambda f: f
     runner.get_dist_info = lambda: (0, 1)
@@ -250,6 +261,40 @@ def gen_full():
     save('full.npz', **out)
 
 
+def dataset_pngs(root):
+    """Two deterministic (input, ref) PNG pairs with sizes that exercise mod-crop and both padding directions."""
+    import cv2
+    os.makedirs(root, exist_ok=True)
+    specs = [('a', (70, 94), (53, 41)), ('b', (48, 40), (66, 90))]      # (H, W) input / ref
+    lines = []
+    for tag, (ih, iw), (rh, rw) in specs:
+        for kind, (h, w), seed in (('in', (ih, iw), 1), ('ref', (rh, rw), 2)):
+            img = (seeding.structured_image(ord(tag) * 10 + seed, 1, max(h, w))[0, :, :h, :w].permute(1, 2, 0).numpy() * 255).round().astype(np.uint8)
+            cv2.imwrite(os.path.join(root, f'{tag}_{kind}.png'), img)
+        lines.append(f'{tag}_in.png {tag}_ref.png')
+    with open(os.path.join(root, 'pairs.txt'), 'w') as f:
+        f.write('\n'.join(lines) + '\n')
+    return os.path.join(root, 'pairs.txt')
+
+
+def gen_dataset():
+    """Test-phase samples of the reference RefCUFEDDataset (mmsr/data/ref_cufed_dataset.py:63-167)."""
+    import tempfile
+    from mmsr.data.ref_cufed_dataset import RefCUFEDDataset
+    out = {}
+    with tempfile.TemporaryDirectory() as root:
+        ann = dataset_pngs(root)
+        ds = RefCUFEDDataset({'dataroot_in': root, 'dataroot_ref': root, 'ann_file': ann, 'io_backend': {'type': 'disk'},
+                              'scale': 4, 'phase': 'test', 'name': 'g'})
+        for i in range(len(ds)):
+            s = ds[i]
+            for k in ('img_in', 'img_in_lq', 'img_in_up', 'img_ref', 'img_ref_lq', 'img_ref_up'):
+                out[f'{i}/{k}'] = s[k].numpy()
+            out[f'{i}/padding'] = np.array(bool(s['padding']))
+            out[f'{i}/original_size'] = np.array(s['original_size'])
+    save('dataset.npz', **out)
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
@@ -258,6 +303,7 @@ def main():
     gen_offsets()
     gen_dcn()
     gen_full()
+    gen_dataset()
     meta = f'torch {torch.__version__}; numpy {np.__version__}; reference 6d60149\n'
     with open(os.path.join(HERE, 'VERSIONS.txt'), 'w') as f:
         f.write(meta)

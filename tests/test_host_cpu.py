@@ -185,3 +185,23 @@ print(json.dumps(out))
     got = json.loads(r.stdout.strip().splitlines()[-1])
     for n, spec in (('g', seeding.spec_restoration_net()), ('e', seeding.spec_extractor()), ('m', seeding.spec_net_map())):
         assert got[n] == {k: list(v) for k, v in spec.items()}
+
+
+def test_dataset_matches_reference_dataset_golden(tmp_path):
+    """N2: the test-phase RefCUFEDDataset (mod-crop, zero-pad to a common size, PIL bicubic /4 and x4,
+    BGR->RGB CHW) reproduces the reference class's samples bit-for-bit (fixture: dataset.npz, minted
+    from mmsr/data/ref_cufed_dataset.py on the same PNGs)."""
+    import numpy as np
+    import make_golden as mg
+    from mmsr.data import create_dataset
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'dataset.npz'))
+    ann = mg.dataset_pngs(str(tmp_path))
+    ds = create_dataset({'type': 'RefCUFEDDataset', 'name': 'g', 'dataroot_in': str(tmp_path), 'dataroot_ref': str(tmp_path),
+                         'ann_file': ann, 'io_backend': {'type': 'disk'}, 'scale': 4, 'phase': 'test'})
+    assert len(ds) == 2
+    for i in range(2):
+        s = ds[i]
+        for k in ('img_in', 'img_in_lq', 'img_in_up', 'img_ref', 'img_ref_lq', 'img_ref_up'):
+            assert np.array_equal(s[k].numpy(), g[f'{i}/{k}']), (i, k)
+        assert bool(s['padding']) == bool(g[f'{i}/padding'])
+        assert list(s['original_size']) == list(g[f'{i}/original_size'])
