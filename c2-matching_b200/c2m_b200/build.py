@@ -6,7 +6,7 @@ PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(PKG_ROOT, 'csrc')
 LIB_DIR = os.path.join(PKG_ROOT, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libc2m_sm100.so')
-SOURCES = ['c_abi.cu', 'corr_aux.cu', 'corr_umma.cu', 'dcn_v2.cu', 'offsets.cu', 'conv3x3_umma.cu', 'dcn_umma.cu']
+SOURCES = ['c_abi.cu', 'corr_aux.cu', 'corr_umma.cu', 'dcn_v2.cu', 'offsets.cu', 'conv3x3_umma.cu', 'dcn_umma.cu', 'dcn_bwd.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC']
 

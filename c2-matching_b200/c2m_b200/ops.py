@@ -400,3 +400,49 @@ def dcn_v2_fused_tc(x, om, weight, bias, deformable_group, pre_offset=None, idx=
     if ret_p is not None and ret_f is not None:
         return ret_p, ret_f
     return ret_p if ret_p is not None else ret_f
+
+
+# ------------------------------------------------------------------------------------------------
+# DCNv2 backward (training; completes the `_ext` ABI)
+def dcn_v2_backward(input, weight, bias, offset, mask, grad_output, kernel_h, kernel_w, stride_h, stride_w, pad_h,
+                    pad_w, dilation_h, dilation_w, deformable_group):
+    """`_ext.dcn_v2_backward` (DCNv2/src/dcn_v2.h:41-72; call site dcn_v2.py:38-47) ->
+    [grad_input, grad_offset, grad_mask, grad_weight, grad_bias].  The deformable pieces
+    (im2col, coordinate/mask gradient, input scatter) are libc2m_sm100 kernels; the two dense
+    GEMMs are torch.matmul in full fp32."""
+    for n, t in (('input', input), ('weight', weight), ('bias', bias), ('offset', offset), ('mask', mask),
+                 ('grad_output', grad_output)):
+        _require_cuda(n, t)
+    x, w = input.contiguous(), weight.contiguous()
+    offset, mask, gout = offset.contiguous(), mask.contiguous(), grad_output.contiguous()
+    B, C, H, W = x.shape
+    cout = w.shape[0]
+    Ho, Wo = _out_hw(H, W, kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h, dilation_w)
+    T, P = kernel_h * kernel_w, Ho * Wo
+    if tuple(gout.shape) != (B, cout, Ho, Wo):
+        raise RuntimeError(f'grad_output has shape {tuple(gout.shape)}, expected {(B, cout, Ho, Wo)}')
+    s = _shape(x, cout, kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h, dilation_w, deformable_group,
+               gout)
+    L = _lib.lib()
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.cuda.device(x.device):
+            w2 = w.view(cout, C * T)
+            g2 = gout.view(B, cout, P)
+            gcol = torch.matmul(w2.t(), g2).contiguous()                          # [B, C*T, P]
+            grad_offset, grad_mask = torch.empty_like(offset), torch.empty_like(mask)
+            _lib.check(L.c2m_dcn_v2_col2im_coord_f32(gcol.data_ptr(), x.data_ptr(), offset.data_ptr(), mask.data_ptr(),
+                                                     s, grad_offset.data_ptr(), grad_mask.data_ptr(), _stream()),
+                       'c2m_dcn_v2_col2im_coord_f32')
+            grad_input = torch.zeros_like(x)
+            _lib.check(L.c2m_dcn_v2_col2im_f32(gcol.data_ptr(), offset.data_ptr(), mask.data_ptr(), s,
+                                               grad_input.data_ptr(), _stream()), 'c2m_dcn_v2_col2im_f32')
+            columns = gcol                                                        # reuse the buffer
+            _lib.check(L.c2m_dcn_v2_im2col_f32(x.data_ptr(), offset.data_ptr(), mask.data_ptr(), s, columns.data_ptr(),
+                                               _stream()), 'c2m_dcn_v2_im2col_f32')
+            grad_weight = torch.matmul(g2, columns.transpose(1, 2)).sum(0).view_as(w)
+            grad_bias = gout.sum(dim=(0, 2, 3))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    return [grad_input, grad_offset, grad_mask, grad_weight, grad_bias]

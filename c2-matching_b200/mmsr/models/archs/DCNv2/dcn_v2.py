@@ -19,14 +19,29 @@ from c2m_b200 import ops as _ops
 logger = logging.getLogger('base')
 
 
-def dcn_v2_conv(input, offset, mask, weight, bias, stride, padding, dilation, deformable_groups):
-    """Forward of the reference's `_DCNv2` autograd Function (dcn_v2.py:16-32)."""
-    if torch.is_grad_enabled() and any(t.requires_grad for t in (input, offset, mask, weight, bias)):
-        raise NotImplementedError('DCNv2 backward is not part of the B200 inference build; '
-                                  'wrap the call in torch.no_grad()')
-    (sh, sw), (ph, pw), (dh, dw) = _pair(stride), _pair(padding), _pair(dilation)
-    return _backend.dcn_v2_forward(input, weight, bias, offset, mask, weight.shape[2], weight.shape[3],
-                                   sh, sw, ph, pw, dh, dw, deformable_groups)
+class _DCNv2(torch.autograd.Function):
+    """The reference's autograd Function (dcn_v2.py:16-50): forward and backward both cross the
+    `_ext` boundary."""
+
+    @staticmethod
+    def forward(ctx, input, offset, mask, weight, bias, stride, padding, dilation, deformable_groups):
+        ctx.geom = (tuple(weight.shape[2:4]), _pair(stride), _pair(padding), _pair(dilation), deformable_groups)
+        (kh, kw), (sh, sw), (ph, pw), (dh, dw), dg = ctx.geom
+        out = _backend.dcn_v2_forward(input, weight, bias, offset, mask, kh, kw, sh, sw, ph, pw, dh, dw, dg)
+        ctx.save_for_backward(input, offset, mask, weight, bias)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_output):
+        input, offset, mask, weight, bias = ctx.saved_tensors
+        (kh, kw), (sh, sw), (ph, pw), (dh, dw), dg = ctx.geom
+        gi, go, gm, gw, gb = _backend.dcn_v2_backward(input, weight, bias, offset, mask, grad_output.contiguous(),
+                                                      kh, kw, sh, sw, ph, pw, dh, dw, dg)
+        return gi, go, gm, gw, gb, None, None, None, None
+
+
+dcn_v2_conv = _DCNv2.apply
 
 
 class DCNv2(nn.Module):
@@ -129,6 +144,15 @@ class DCN_sep_pre_multi_offset(_WithOffsetConv):
             mean = om[:, :om.shape[1] // 3 * 2].abs().mean()
             if mean > 100:
                 logger.warning(f'Offset mean is {mean}, larger than 100.')
+        if torch.is_grad_enabled() and (om.requires_grad or x.requires_grad or self.weight.requires_grad):
+            # training: the reference's differentiable formulation (dcn_v2.py:231-253) over dcn_v2_conv
+            pre = pre_offset.materialize() if hasattr(pre_offset, 'materialize') else pre_offset
+            n = om.shape[1] // 3
+            reord = torch.stack((pre[..., 1], pre[..., 0]), dim=2).flatten(1, 2).repeat(1, self.deformable_groups, 1, 1)
+            out = dcn_v2_conv(x, om[:, :2 * n] + reord, torch.sigmoid(om[:, 2 * n:]), self.weight, self.bias,
+                              self.stride, self.padding, self.dilation, self.deformable_groups)
+            out = out if lrelu_slope == 1.0 else torch.nn.functional.leaky_relu(out, lrelu_slope)
+            return _ops.psa_from_f32(out) if want_psa else out
         idx = getattr(pre_offset, 'max_idx', None)
         kw = dict(idx=idx, pre_scale=pre_offset.scale, ref_gw=pre_offset.ref_gw) if idx is not None else \
             dict(pre_offset=pre_offset)          # ScaleOffsets handle: no offset pyramid in HBM

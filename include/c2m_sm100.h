@@ -163,6 +163,21 @@ size_t c2m_dcn_tc_packed_weight_bytes(int C, int Cout, int dg);
 int c2m_dcn_tc_pack_weights_f32(const float *w, int C, int Cout, int dg, void *packed, c2m_stream_t stream);
 int c2m_dcn_v2_fused_tc(const c2m_dcn_tc_args *args, c2m_stream_t stream);
 
+/* --- DCNv2 backward building blocks (`_ext.dcn_v2_backward`, DCNv2/src/dcn_v2.h:41-72) -----------
+ * All tensors fp32, NCHW-contiguous; shape->x* / o* strides are ignored here.
+ *   columns [B, C*kh*kw, Ho*Wo] = mask * bilinear(x)                      (for grad_weight = gout x columns^T)
+ *   gcol    [B, C*kh*kw, Ho*Wo] = W^T x grad_output                       (computed by the caller)
+ *   grad_offset [B,2*dg*kh*kw,Ho,Wo], grad_mask [B,dg*kh*kw,Ho,Wo] written; grad_input [B,C,H,W] ACCUMULATED
+ *   (caller zero-fills it first).
+ */
+int c2m_dcn_v2_im2col_f32(const float *x, const float *offset, const float *mask, const c2m_dcn_shape *shape,
+                          float *columns, c2m_stream_t stream);
+int c2m_dcn_v2_col2im_coord_f32(const float *gcol, const float *x, const float *offset, const float *mask,
+                                const c2m_dcn_shape *shape, float *grad_offset, float *grad_mask,
+                                c2m_stream_t stream);
+int c2m_dcn_v2_col2im_f32(const float *gcol, const float *offset, const float *mask, const c2m_dcn_shape *shape,
+                          float *grad_input, c2m_stream_t stream);
+
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 unsigned long long c2m_launch_count(void);
 

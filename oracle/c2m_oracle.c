@@ -241,3 +241,85 @@ int oracle_channel_l2norm(const float *x, float *y, int C, long HW)
     }
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * _ext.dcn_v2_backward — DCNv2/src/cuda/dcn_v2_cuda.cu:206-335 with the col2im / col2im_coord
+ * kernels (dcn_v2_im2col_cuda.cu:56-123 weights, :197-254 grad_input, :256-327 grad_offset/mask).
+ *
+ *   gcol[b,ck,p]   = sum_o W[o,ck] * gout[b,o,p]                                        (:265-268)
+ *   grad_mask      = sum_{c in g} gcol * bilinear(x[b,c], pos)       (0 outside (-1,H)x(-1,W), :300-307)
+ *   grad_offset_h/w= sum_{c in g} gcol * mask * d bilinear / d h|w   (dmcn_get_coordinate_weight, :83-123)
+ *   grad_input    += gcol * mask * bilinear corner weight, in-bounds corners only      (:233-252, :56-80)
+ *   grad_weight[o,ck] = sum_{b,p} gout[b,o,p] * columns[b,ck,p];  grad_bias[o] = sum_{b,p} gout   (:296-330)
+ * All accumulations in double.
+ * ------------------------------------------------------------------------------------------ */
+int oracle_dcn_v2_backward(const float *x, const float *weight, const float *offset, const float *mask,
+                           const float *gout, float *gx, float *goff, float *gmask, float *gw, float *gb,
+                           int B, int C, int H, int W, int Cout, int kh, int kw, int sh, int sw,
+                           int ph, int pw, int dh, int dw, int dg)
+{
+    if (dg <= 0 || C % dg) return 1;
+    const int Ho = (H + 2 * ph - (dh * (kh - 1) + 1)) / sh + 1;
+    const int Wo = (W + 2 * pw - (dw * (kw - 1) + 1)) / sw + 1;
+    const int T = kh * kw, K = C * T, cpg = C / dg;
+    const long P = (long)Ho * Wo;
+    double *dgx = (double *)calloc((size_t)B * C * H * W, sizeof(double));
+    double *dgw = (double *)calloc((size_t)Cout * K, sizeof(double));
+    double *dgb = (double *)calloc((size_t)Cout, sizeof(double));
+    if (!dgx || !dgw || !dgb) return 2;
+    for (int b = 0; b < B; ++b)
+        for (long p = 0; p < P; ++p) {
+            const int ho = (int)(p / Wo), wo = (int)(p % Wo);
+            for (int o = 0; o < Cout; ++o) dgb[o] += gout[((long)b * Cout + o) * P + p];
+            for (int g = 0; g < dg; ++g)
+                for (int k = 0; k < T; ++k) {
+                    const int i = k / kw, j = k % kw;
+                    const float oh = offset[(((long)b * dg + g) * 2 * T + 2 * k) * P + p];
+                    const float ow = offset[(((long)b * dg + g) * 2 * T + 2 * k + 1) * P + p];
+                    const float m = mask[(((long)b * dg + g) * T + k) * P + p];
+                    const float h_im = (float)(ho * sh - ph + i * dh) + oh;
+                    const float w_im = (float)(wo * sw - pw + j * dw) + ow;
+                    const int valid = h_im > -1 && w_im > -1 && h_im < H && w_im < W;
+                    double acc_h = 0, acc_w = 0, acc_m = 0;
+                    const int hl = (int)floorf(h_im), wl = (int)floorf(w_im), hh_ = hl + 1, wh = wl + 1;
+                    const double lh = (double)h_im - hl, lw = (double)w_im - wl;
+                    for (int cl = 0; cl < cpg; ++cl) {
+                        const int c = g * cpg + cl, ck = c * T + k;
+                        double gc = 0;
+                        for (int o = 0; o < Cout; ++o) gc += (double)weight[(long)o * K + ck] * gout[((long)b * Cout + o) * P + p];
+                        const float *im = x + ((long)b * C + c) * H * W;
+                        double v1 = 0, v2 = 0, v3 = 0, v4 = 0;
+                        if (valid) {
+                            if (hl >= 0 && wl >= 0) v1 = im[hl * W + wl];
+                            if (hl >= 0 && wh <= W - 1) v2 = im[hl * W + wh];
+                            if (hh_ <= H - 1 && wl >= 0) v3 = im[hh_ * W + wl];
+                            if (hh_ <= H - 1 && wh <= W - 1) v4 = im[hh_ * W + wh];
+                        }
+                        const double val = (1 - lh) * (1 - lw) * v1 + (1 - lh) * lw * v2 + lh * (1 - lw) * v3 + lh * lw * v4;
+                        /* columns entry for grad_weight */
+                        const double col = valid ? val * m : 0.0;
+                        for (int o = 0; o < Cout; ++o) dgw[(long)o * K + ck] += (double)gout[((long)b * Cout + o) * P + p] * col;
+                        if (valid) {
+                            acc_m += gc * val;
+                            /* d/dh: -(1-lw) v1 - lw v2 + (1-lw) v3 + lw v4 ; d/dw: -(1-lh) v1 + (1-lh) v2 - lh v3 + lh v4 */
+                            acc_h += gc * m * (-(1 - lw) * v1 - lw * v2 + (1 - lw) * v3 + lw * v4);
+                            acc_w += gc * m * (-(1 - lh) * v1 + (1 - lh) * v2 - lh * v3 + lh * v4);
+                            const double tg = gc * m;
+                            double *gim = dgx + ((long)b * C + c) * H * W;
+                            if (hl >= 0 && wl >= 0) gim[hl * W + wl] += tg * (1 - lh) * (1 - lw);
+                            if (hl >= 0 && wh <= W - 1) gim[hl * W + wh] += tg * (1 - lh) * lw;
+                            if (hh_ <= H - 1 && wl >= 0) gim[hh_ * W + wl] += tg * lh * (1 - lw);
+                            if (hh_ <= H - 1 && wh <= W - 1) gim[hh_ * W + wh] += tg * lh * lw;
+                        }
+                    }
+                    goff[(((long)b * dg + g) * 2 * T + 2 * k) * P + p] = (float)acc_h;
+                    goff[(((long)b * dg + g) * 2 * T + 2 * k + 1) * P + p] = (float)acc_w;
+                    gmask[(((long)b * dg + g) * T + k) * P + p] = (float)acc_m;
+                }
+        }
+    for (long i = 0; i < (long)B * C * H * W; ++i) gx[i] = (float)dgx[i];
+    for (long i = 0; i < (long)Cout * K; ++i) gw[i] = (float)dgw[i];
+    for (int o = 0; o < Cout; ++o) gb[o] = (float)dgb[o];
+    free(dgx); free(dgw); free(dgb);
+    return 0;
+}

@@ -88,3 +88,18 @@ def channel_l2norm(x):
     lib().oracle_channel_l2norm(_p(x, ctypes.c_float), _p(y, ctypes.c_float), x.shape[0],
                                 ctypes.c_long(x[0].numel()))
     return y
+
+
+def dcn_v2_backward(x, weight, bias, offset, mask, grad_output, kh=3, kw=3, sh=1, sw=1, ph=1, pw=1, dh=1, dw=1, dg=8):
+    x, weight, offset, mask, grad_output = [t.contiguous().float() for t in (x, weight, offset, mask, grad_output)]
+    b, c, h, w = x.shape
+    cout = weight.shape[0]
+    gx, goff, gm = torch.empty_like(x), torch.empty_like(offset), torch.empty_like(mask)
+    gw, gb = torch.empty_like(weight), torch.empty(cout)
+    rc = lib().oracle_dcn_v2_backward(
+        _p(x, ctypes.c_float), _p(weight, ctypes.c_float), _p(offset, ctypes.c_float), _p(mask, ctypes.c_float),
+        _p(grad_output, ctypes.c_float), _p(gx, ctypes.c_float), _p(goff, ctypes.c_float), _p(gm, ctypes.c_float),
+        _p(gw, ctypes.c_float), _p(gb, ctypes.c_float), b, c, h, w, cout, kh, kw, sh, sw, ph, pw, dh, dw, dg)
+    if rc:
+        raise RuntimeError(f'oracle_dcn_v2_backward rc={rc}')
+    return gx, goff, gm, gw, gb

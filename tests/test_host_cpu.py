@@ -75,8 +75,8 @@ def test_cpu_tensors_fail_loudly():
                             torch.zeros(1, 9, 6, 6), 3, 3, 1, 1, 1, 1, 1, 1, 1)
     with pytest.raises(RuntimeError, match='CUDA tensor'):
         feature_match_index(torch.zeros(8, 6, 6), torch.zeros(8, 6, 6))
-    with pytest.raises(NotImplementedError):
-        _ext.dcn_v2_backward(*([None] * 15))
+    with pytest.raises((RuntimeError, TypeError)):
+        _ext.dcn_v2_backward(*([x] * 6), 3, 3, 1, 1, 1, 1, 1, 1, 1)
 
 
 def test_feature_match_index_signature():

@@ -144,3 +144,28 @@ def test_full_forward_port(tag, golden):
     assert np.array_equal(idx.numpy(), g[tag + '/max_idx'])
     np.testing.assert_allclose(sr.numpy(), g[tag + '/sr'], rtol=1e-4, atol=1e-4)
     assert g[tag + '/gap64'].shape == idx.shape
+
+
+@pytest.mark.parametrize('cfg', [(2, 8, 6, 9, 7, 2, 3, 1, 1, 1), (1, 12, 10, 8, 10, 4, 3, 2, 2, 2), (1, 6, 4, 7, 6, 1, 5, 1, 2, 1)])
+def test_dcn_backward_oracle_equals_torch_autograd(cfg):
+    """Literal restatement of the reference backward == autograd through torchvision's CPU
+    deform_conv2d (fp64), incl. offsets that leave the image, stride/dilation and a 5x5 kernel.
+    Offsets are kept away from integer positions, where the bilinear derivative is one-sided."""
+    B, C, cout, H, W, dg, ks, st, pad, dil = cfg
+    T = ks * ks
+    ho, wo = (H + 2 * pad - (dil * (ks - 1) + 1)) // st + 1, (W + 2 * pad - (dil * (ks - 1) + 1)) // st + 1
+    x = seeding.randn(1, (B, C, H, W))
+    wgt = seeding.randn(2, (cout, C, ks, ks), 0.2)
+    bias = seeding.randn(3, (cout,))
+    off = seeding.randn(4, (B, 2 * dg * T, ho, wo), 2.5)
+    off = torch.where((off - off.round()).abs() < 0.05, off + 0.11, off)
+    mask = torch.sigmoid(seeding.randn(5, (B, dg * T, ho, wo)))
+    gout = seeding.randn(6, (B, cout, ho, wo))
+    leaves = [t.double().requires_grad_(True) for t in (x, wgt, bias, off, mask)]
+    y = ref_path.dcn_v2_forward(leaves[0], leaves[1], leaves[2], leaves[3], leaves[4], ks, ks, st, st, pad, pad, dil, dil, dg)
+    y.backward(gout.double())
+    gx, goff, gm, gw, gb = c_oracle.dcn_v2_backward(x, wgt, bias, off, mask, gout, ks, ks, st, st, pad, pad, dil, dil, dg)
+    for got, leaf, name in ((gx, leaves[0], 'input'), (gw, leaves[1], 'weight'), (gb, leaves[2], 'bias'),
+                            (goff, leaves[3], 'offset'), (gm, leaves[4], 'mask')):
+        want = leaf.grad.float()
+        assert float((got - want).abs().max()) <= 2e-5 * max(1.0, float(want.abs().max())), name
