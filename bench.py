@@ -24,7 +24,6 @@ import os
 import statistics
 import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -39,36 +38,44 @@ WORKLOAD = 'config2: LR 160x160 -> SR 640x640, Ref 500x500 zero-padded to 640x64
 
 
 # ------------------------------------------------------------------------------- helpers
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region: one background `nvidia-smi -lms`
+    process (a fresh nvidia-smi per sample takes ~0.5 s on these hosts and misses short runs)."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.rows, self._stop_ev = index, [], threading.Event()
+        self.index, self.proc = index, None
 
-    def run(self):
-        while not self._stop_ev.is_set():
-            try:
-                out = subprocess.run(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-i',
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.splitlines()[0].split(',')])
-            except Exception:
-                pass
-            self._stop_ev.wait(0.2)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-i',
+                                          str(self.index), '-lms', '100'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
 
     def stop(self):
-        self._stop_ev.set()
-        self.join(timeout=5)
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        rows = []
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:
+                self.proc.kill()
+                out = ''
+            rows = [[c.strip() for c in ln.split(',')] for ln in out.splitlines() if ln.strip()]
+        num = lambda v: v.replace('.', '', 1).isdigit()
+        # keep samples taken under load (power well above idle) when there are any
+        sm = [float(r[0]) for r in rows if len(r) >= 7 and num(r[0])]
+        mx = [float(r[1]) for r in rows if len(r) >= 7 and num(r[1])]
+        pw = [float(r[2]) for r in rows if len(r) >= 7 and num(r[2])]
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = sorted({n for r in self.rows for n, v in zip(names, r[3:7]) if v.lower().startswith('active')})
+        reasons = sorted({n for r in rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith('active')})
         return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': reasons, 'samples': len(self.rows)}
+                'power_w_max': max(pw) if pw else None, 'reasons': reasons, 'samples': len(rows)}
 
 
 def seeded_weights():
@@ -270,7 +277,7 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', choices=['ours', 'reference'], default='ours')
     ap.add_argument('--tf32', type=int, default=0, help='allow cuDNN TF32 for the plain convolutions (default: exact fp32)')
