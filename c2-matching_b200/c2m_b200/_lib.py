@@ -59,6 +59,7 @@ SYMBOLS = {
     'c2m_psa_to_f32': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 5 + [c_f32p, c_f32p] +
                        [ctypes.c_longlong] * 4 + [ctypes.c_void_p]),
     'c2m_conv3x3': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    'c2m_psa_maxpool2': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 4 + [ctypes.c_void_p] * 3),
     'c2m_dcn_v2_im2col_f32': (ctypes.c_int, [c_f32p] * 3 + [ctypes.POINTER(DcnShape), c_f32p, ctypes.c_void_p]),
     'c2m_dcn_v2_col2im_coord_f32': (ctypes.c_int, [c_f32p] * 4 + [ctypes.POINTER(DcnShape), c_f32p, c_f32p, ctypes.c_void_p]),
     'c2m_dcn_v2_col2im_f32': (ctypes.c_int, [c_f32p] * 3 + [ctypes.POINTER(DcnShape), c_f32p, ctypes.c_void_p]),

@@ -238,6 +238,16 @@ def psa_to_f32(p, add=None, channels_last=False):
     return out
 
 
+def psa_maxpool2(p):
+    """nn.MaxPool2d(kernel_size=2, stride=2) on a PSA tensor."""
+    out = PSA.empty(p.B, p.C, p.H // 2, p.W // 2, p.hi.device, p.sa)
+    with torch.cuda.device(p.hi.device):
+        rc = _lib.lib().c2m_psa_maxpool2(p.hi.data_ptr(), p.lo.data_ptr(), p.B, p.C, p.H, p.W, out.hi.data_ptr(),
+                                         out.lo.data_ptr(), _stream())
+        _lib.check(rc, 'c2m_psa_maxpool2')
+    return out
+
+
 def conv3x3_supported(cin, cout, H=None, W=None):
     """The tcgen05 kernel takes any channel counts; maps must hold one halo tile (18 x 10)."""
     return H is None or (H >= 18 and W >= 10)

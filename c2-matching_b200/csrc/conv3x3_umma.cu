@@ -313,6 +313,45 @@ __global__ void psa_to_f32_kernel(const __half *__restrict__ hi, const __half *_
     }
 }
 
+// 2x2 / stride 2 max-pool on a PSA tensor (VGG pool1/pool2 between tcgen05 convolutions): the
+// pooled map stays in the operand layout, no fp32 round trip through HBM.  max(hi+lo) is taken on
+// the reconstructed fp32 values and re-split (the re-split of an already-split value is exact).
+__global__ void psa_maxpool2_kernel(const __half *__restrict__ hi, const __half *__restrict__ lo, int C8, int H, int W,
+                                    __half *__restrict__ ohi, __half *__restrict__ olo) {
+    const int Ho = H / 2, Wo = W / 2;
+    const long long n = (long long)C8 * Ho * Wo;
+    const int b = blockIdx.y;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const int xo = (int)(e % Wo), yo = (int)((e / Wo) % Ho), oct = (int)(e / ((long long)Wo * Ho));
+        float m[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                const size_t o = ((((size_t)b * C8 + oct) * H + 2 * yo + dy) * W + 2 * xo + dx) * 8;
+                const uint4 rh = *reinterpret_cast<const uint4 *>(hi + o);
+                const uint4 rl = *reinterpret_cast<const uint4 *>(lo + o);
+                const __half *hh = reinterpret_cast<const __half *>(&rh);
+                const __half *ll = reinterpret_cast<const __half *>(&rl);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], __half2float(hh[j]) + __half2float(ll[j]));
+            }
+        __align__(16) __half h8[8];
+        __align__(16) __half l8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const __half hq = __float2half_rn(m[j]);
+            h8[j] = hq;
+            l8[j] = __float2half_rn(m[j] - __half2float(hq));
+        }
+        const size_t oo = ((((size_t)b * C8 + oct) * Ho + yo) * Wo + xo) * 8;
+        *reinterpret_cast<uint4 *>(ohi + oo) = *reinterpret_cast<const uint4 *>(h8);
+        *reinterpret_cast<uint4 *>(olo + oo) = *reinterpret_cast<const uint4 *>(l8);
+    }
+}
+
 __global__ void wamax_kernel(const float *__restrict__ w, int n, unsigned *__restrict__ bits) {
     float m = 0.f;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = fmaxf(m, fabsf(w[i]));
@@ -437,6 +476,20 @@ extern "C" int c2m_psa_to_f32(const void *hi, const void *lo, int B, int C, int 
         reinterpret_cast<const __half *>(hi), reinterpret_cast<const __half *>(lo), C, C8, H, W, sa, add, out, os_b,
         os_c, os_y, os_x);
     C2M_LAUNCH_CHECK("psa_to_f32_kernel");
+    return C2M_OK;
+}
+
+extern "C" int c2m_psa_maxpool2(const void *hi, const void *lo, int B, int C, int H, int W, void *out_hi, void *out_lo,
+                                c2m_stream_t stream) {
+    C2M_CHECK_ARG(hi && lo && out_hi && out_lo && B > 0 && C > 0 && H >= 2 && W >= 2, "psa_maxpool2: bad argument");
+    const int C8 = (C + 7) / 8;
+    const long long n = (long long)C8 * (H / 2) * (W / 2);
+    int bx = (int)((n + 255) / 256);
+    if (bx > 4096) bx = 4096;
+    psa_maxpool2_kernel<<<dim3(bx, B), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __half *>(hi), reinterpret_cast<const __half *>(lo), C8, H, W,
+        reinterpret_cast<__half *>(out_hi), reinterpret_cast<__half *>(out_lo));
+    C2M_LAUNCH_CHECK("psa_maxpool2_kernel");
     return C2M_OK;
 }
 

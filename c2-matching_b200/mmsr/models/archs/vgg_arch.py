@@ -94,8 +94,9 @@ def run_trunk(trunk, x, taps=(), want_last_f32=True):
             out_name = layers[i + 1][0] if has_relu else name
             nxt = layers[i + 2][1] if has_relu and i + 2 < len(layers) else (layers[i + 1][1] if not has_relu and i + 1 < len(layers) else None)
             last = nxt is None
-            need_f32 = out_name in taps or isinstance(nxt, nn.MaxPool2d) or (last and want_last_f32)
-            need_psa = isinstance(nxt, nn.Conv2d) or out_name in taps
+            pool_next = isinstance(nxt, nn.MaxPool2d) and nxt.kernel_size in (2, (2, 2)) and nxt.stride in (2, (2, 2))
+            need_f32 = out_name in taps or (isinstance(nxt, nn.MaxPool2d) and not pool_next) or (last and want_last_f32)
+            need_psa = isinstance(nxt, nn.Conv2d) or out_name in taps or pool_next
             if xp is None:
                 xp = ops.psa_from_f32(xf)
             # tapped features feed the DCN sampler, which gathers 8-channel octets: keep them channels-last
@@ -112,8 +113,11 @@ def run_trunk(trunk, x, taps=(), want_last_f32=True):
                 got[out_name] = xf
             i += 2 if has_relu else 1
         elif isinstance(layer, nn.MaxPool2d):
-            xf = layer(xf)
-            xp = None
+            if xp is not None and layer.kernel_size in (2, (2, 2)) and layer.stride in (2, (2, 2)):
+                xp, xf = ops.psa_maxpool2(xp), None          # stays in the operand layout
+            else:
+                xf = layer(xf if xf is not None else ops.psa_to_f32(xp))
+                xp = None
             i += 1
         else:
             raise RuntimeError(f'unexpected layer {name} in VGG trunk')

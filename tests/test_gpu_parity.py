@@ -495,3 +495,26 @@ def test_dcn_sep_pre_multi_offset_trains(golden):
     y.square().mean().backward()
     for p_ in (m.weight, m.bias, m.conv_offset_mask.weight):
         assert p_.grad is not None and torch.isfinite(p_.grad).all() and float(p_.grad.abs().sum()) > 0
+
+
+def test_psa_maxpool_and_vgg_trunk_fast_path():
+    from c2m_b200 import ops
+    from mmsr.models.archs.vgg_arch import VGGFeatureExtractor
+    x = seeding.randn(71, (2, 24, 38, 46), 2.0).to(DEV)
+    got = ops.psa_to_f32(ops.psa_maxpool2(ops.psa_from_f32(x)))
+    want = F.max_pool2d(x, 2, 2)
+    assert float((got - want).abs().max()) <= 2e-6 * float(want.abs().max())
+    net = VGGFeatureExtractor(['relu1_1', 'relu2_1', 'relu3_1'], 'vgg19')
+    net.load_state_dict(seeding.seeded_state_dict({k: tuple(v.shape) for k, v in net.state_dict().items()}, 5))
+    net.to(DEV).eval()
+    img = seeding.rand_image(72, (1, 3, 96, 80)).to(DEV)
+    with torch.no_grad():
+        fast = net(img)
+        xn = (img - net.mean) / net.std
+        slow = {}
+        for name, layer in net.vgg_net.named_children():
+            xn = torch.relu(xn) if isinstance(layer, torch.nn.ReLU) else layer(xn)
+            if name in ('relu1_1', 'relu2_1', 'relu3_1'):
+                slow[name] = xn
+    for k in slow:
+        _rel_ok(fast[k], slow[k], 2e-5)
