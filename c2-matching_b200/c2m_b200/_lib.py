@@ -36,8 +36,7 @@ class ConvArgs(ctypes.Structure):
 
 class DcnTcArgs(ctypes.Structure):
     """c2m_dcn_tc_args (include/c2m_sm100.h)."""
-    _fields_ = [('x', ctypes.c_void_p), ('xs_b', ctypes.c_longlong), ('xs_c', ctypes.c_longlong),
-                ('xs_y', ctypes.c_longlong), ('xs_x', ctypes.c_longlong),
+    _fields_ = [('x_hi', ctypes.c_void_p), ('x_lo', ctypes.c_void_p),
                 ('om', ctypes.c_void_p), ('pre', ctypes.c_void_p), ('idx', ctypes.c_void_p),
                 ('gh', ctypes.c_int), ('gw', ctypes.c_int), ('ref_gw', ctypes.c_int), ('pre_scale', ctypes.c_int),
                 ('B', ctypes.c_int), ('C', ctypes.c_int), ('H', ctypes.c_int), ('W', ctypes.c_int),

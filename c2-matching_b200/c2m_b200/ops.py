@@ -365,18 +365,24 @@ def dcn_v2_fused_tc(x, om, weight, bias, deformable_group, pre_offset=None, idx=
                     lrelu=False, psa_out=False, out_f32=True, channels_last_out=False):
     """Tensor-core version of dcn_v2_fused_forward (3x3/s1/p1/d1).  Returns fp32 and / or PSA."""
     import ctypes
-    _require_cuda('x', x)
     _require_cuda('om', om)
-    B, C, H, W = x.shape
+    if isinstance(x, PSA):
+        xp = x
+    else:
+        _require_cuda('x', x)
+        xp = getattr(x, '_c2m_psa', None)
+        if xp is None or xp.shape != tuple(x.shape):
+            xp = psa_from_f32(x)
+    if xp.sa != 0:
+        raise RuntimeError('dcn_v2_fused_tc: PSA input must have scale exponent 0')
+    B, C, H, W = xp.shape
+    dev = xp.hi.device
     cout = weight.shape[0]
-    if not x.is_contiguous(memory_format=torch.channels_last):
-        x = x.contiguous(memory_format=torch.channels_last)
     om = om.contiguous()
     if tuple(om.shape) != (B, 27 * deformable_group, H, W):
         raise RuntimeError(f'conv_offset_mask output has shape {tuple(om.shape)}')
     a = _lib.DcnTcArgs()
-    a.x = x.data_ptr()
-    a.xs_b, a.xs_c, a.xs_y, a.xs_x = x.stride()
+    a.x_hi, a.x_lo = xp.hi.data_ptr(), xp.lo.data_ptr()
     a.om = om.data_ptr()
     if pre_offset is not None:
         _require_cuda('pre_offset', pre_offset)
@@ -397,14 +403,14 @@ def dcn_v2_fused_tc(x, om, weight, bias, deformable_group, pre_offset=None, idx=
     a.lrelu = int(bool(lrelu))
     ret_p = ret_f = None
     if psa_out:
-        ret_p = PSA.empty(B, cout, H, W, x.device)
+        ret_p = PSA.empty(B, cout, H, W, dev)
         a.out_hi, a.out_lo, a.sa_out = ret_p.hi.data_ptr(), ret_p.lo.data_ptr(), 0
     if out_f32:
         mf = torch.channels_last if channels_last_out else torch.contiguous_format
-        ret_f = torch.empty(B, cout, H, W, dtype=torch.float32, device=x.device, memory_format=mf)
+        ret_f = torch.empty(B, cout, H, W, dtype=torch.float32, device=dev, memory_format=mf)
         a.out_f32 = ret_f.data_ptr()
         a.os_b, a.os_c, a.os_y, a.os_x = ret_f.stride()
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(dev):
         rc = _lib.lib().c2m_dcn_v2_fused_tc(ctypes.addressof(a), _stream())
         _lib.check(rc, 'c2m_dcn_v2_fused_tc')
     if ret_p is not None and ret_f is not None:

@@ -13,7 +13,7 @@
 //   the tcgen05 K-major no-swizzle layout (hi and lo halves): per (pixel, g, tap) the sampling point
 //   is computed once (raw conv_offset_mask output + pre-offset rebuilt from the index map or read
 //   from the pre_offset tensor, sigmoid mask, validity of the 4 corners), the 8 channels of an octet
-//   are fetched as 2 x 16 B per corner from the channels-last fp32 input, blended in fp32,
+//   are fetched as 16 B (hi) + 16 B (lo) per corner from the octet-planar PSA input, blended in fp32,
 //   multiplied by the mask, split and stored with one 16 B st.shared per half;
 //   fence.proxy.async + mbarrier hand the stage to the MMA-issuing thread.
 //   Weights stream as 8 KB chunks (bulk copy, 4-deep ring), shared by the item's 8 pixel tiles
@@ -37,8 +37,8 @@ constexpr int NGATHER_WARPS = 8;
 constexpr int W_HDR = 256;
 
 struct DcnTc {
-    const float *x;            // channels-last addressing via element strides
-    long long xs_b, xs_c, xs_y, xs_x;
+    const __half *x_hi, *x_lo; // input in the packed-split layout [B][C/8][H][W][8] (value = hi + lo)
+    int C8;
     const float *om;           // [B, 3*dg*9, H, W]
     const float *pre;          // [B, 9, H, W, 2] or null
     const long long *idx;      // [B, gh, gw] or null
@@ -201,7 +201,8 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             int b, t0, nt, slice;
             decode(item, b, t0, nt, slice);
-            const float *xb = d.x + (long long)b * d.xs_b;
+            const __half *xh = d.x_hi + (size_t)b * d.C8 * p.H * p.W * 8;
+            const __half *xl = d.x_lo + (size_t)b * d.C8 * p.H * p.W * 8;
             const float *omb = d.om + (long long)b * 3 * d.dg * 9 * P;
             const long long *idxb = d.idx ? d.idx + (long long)b * d.gh * d.gw : nullptr;
             const float *preb = d.pre ? d.pre + (long long)b * 9 * P * 2 : nullptr;
@@ -272,23 +273,27 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
                             const float lh = h_im - h_low, lw = w_im - w_low;
                             const float hh = 1.f - lh, hw = 1.f - lw;
                             const bool tv = h_low >= 0, bv = h_high <= p.H - 1, lvv = w_low >= 0, rv = w_high <= p.W - 1;
-                            const int cbase = g * d.cpg + (oh * 2 + u + kc * KOCT - pr[u] * d.opp) * 8;
-                            if (tv && lvv) { o[u][0] = (int)(h_low * d.xs_y + w_low * d.xs_x) + cbase; wq[u][0] = hh * hw; }
-                            if (tv && rv) { o[u][1] = (int)(h_low * d.xs_y + w_high * d.xs_x) + cbase; wq[u][1] = hh * lw; }
-                            if (bv && lvv) { o[u][2] = (int)(h_high * d.xs_y + w_low * d.xs_x) + cbase; wq[u][2] = lh * hw; }
-                            if (bv && rv) { o[u][3] = (int)(h_high * d.xs_y + w_high * d.xs_x) + cbase; wq[u][3] = lh * lw; }
+                            // channel octet of this K octet, as an element offset of its [H][W][8] plane
+                            const int oct_c = g * (d.cpg / 8) + (oh * 2 + u + kc * KOCT - pr[u] * d.opp);
+                            const int cbase = oct_c * p.H * p.W * 8;
+                            if (tv && lvv) { o[u][0] = (h_low * p.W + w_low) * 8 + cbase; wq[u][0] = hh * hw; }
+                            if (tv && rv) { o[u][1] = (h_low * p.W + w_high) * 8 + cbase; wq[u][1] = hh * lw; }
+                            if (bv && lvv) { o[u][2] = (h_high * p.W + w_low) * 8 + cbase; wq[u][2] = lh * hw; }
+                            if (bv && rv) { o[u][3] = (h_high * p.W + w_high) * 8 + cbase; wq[u][3] = lh * lw; }
                             mk[u] = 1.f / (1.f + expf(-mt[u].mr));
                         }
                     }
                 }
                 // ---- corner fetches of both octets in flight together, then the next stage's metadata
-                float4 cv[2][4][2];
+                // octet-planar operand: the 32 lanes of a warp (4 rows x 8 pixels) read 16 B each from runs of
+                // adjacent pixels (8 lines per request instead of 32 with a channels-last fp32 input)
+                uint4 ch[2][4], cl[2][4];
 #pragma unroll
                 for (int u = 0; u < 2; ++u)
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                        cv[u][c][0] = *reinterpret_cast<const float4 *>(xb + o[u][c]);
-                        cv[u][c][1] = *reinterpret_cast<const float4 *>(xb + o[u][c] + 4);
+                        ch[u][c] = *reinterpret_cast<const uint4 *>(xh + o[u][c]);
+                        cl[u][c] = *reinterpret_cast<const uint4 *>(xl + o[u][c]);
                     }
                 fetch(step + 1, 0, nx[0], npr[0], nlv[0]);
                 fetch(step + 1, 1, nx[1], npr[1], nlv[1]);
@@ -298,19 +303,22 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
                 for (int u = 0; u < 2; ++u) {
                     __align__(16) __half h8[8];
                     __align__(16) __half l8[8];
+                    const __half *hp[4], *lp[4];
 #pragma unroll
-                    for (int hh2 = 0; hh2 < 2; ++hh2) {
-                        const float a4[4] = {cv[u][0][hh2].x, cv[u][0][hh2].y, cv[u][0][hh2].z, cv[u][0][hh2].w};
-                        const float b4[4] = {cv[u][1][hh2].x, cv[u][1][hh2].y, cv[u][1][hh2].z, cv[u][1][hh2].w};
-                        const float c4[4] = {cv[u][2][hh2].x, cv[u][2][hh2].y, cv[u][2][hh2].z, cv[u][2][hh2].w};
-                        const float d4[4] = {cv[u][3][hh2].x, cv[u][3][hh2].y, cv[u][3][hh2].z, cv[u][3][hh2].w};
+                    for (int c = 0; c < 4; ++c) {
+                        hp[c] = reinterpret_cast<const __half *>(&ch[u][c]);
+                        lp[c] = reinterpret_cast<const __half *>(&cl[u][c]);
+                    }
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float v = (wq[u][0] * a4[j] + wq[u][1] * b4[j] + wq[u][2] * c4[j] + wq[u][3] * d4[j]) * mk[u];
-                            const __half hq = __float2half_rn(v);
-                            h8[hh2 * 4 + j] = hq;
-                            l8[hh2 * 4 + j] = __float2half_rn(v - __half2float(hq));
-                        }
+                    for (int j = 0; j < 8; ++j) {
+                        const float a = __half2float(hp[0][j]) + __half2float(lp[0][j]);
+                        const float bq = __half2float(hp[1][j]) + __half2float(lp[1][j]);
+                        const float cq = __half2float(hp[2][j]) + __half2float(lp[2][j]);
+                        const float dq = __half2float(hp[3][j]) + __half2float(lp[3][j]);
+                        const float v = (wq[u][0] * a + wq[u][1] * bq + wq[u][2] * cq + wq[u][3] * dq) * mk[u];
+                        const __half hq = __float2half_rn(v);
+                        h8[j] = hq;
+                        l8[j] = __float2half_rn(v - __half2float(hq));
                     }
                     h_out[u] = *reinterpret_cast<const uint4 *>(h8);
                     l_out[u] = *reinterpret_cast<const uint4 *>(l8);
@@ -422,12 +430,9 @@ extern "C" int c2m_dcn_tc_pack_weights_f32(const float *w, int C, int Cout, int 
 }
 
 extern "C" int c2m_dcn_v2_fused_tc(const c2m_dcn_tc_args *a, c2m_stream_t stream) {
-    C2M_CHECK_ARG(a && a->x && a->om && a->packed_w, "dcn_v2_fused_tc: null pointer");
+    C2M_CHECK_ARG(a && a->x_hi && a->x_lo && a->om && a->packed_w, "dcn_v2_fused_tc: null pointer");
     C2M_CHECK_ARG(a->B > 0 && a->H > 0 && a->W > 0, "dcn_v2_fused_tc: bad shape");
     C2M_CHECK_ARG(c2m_dcn_tc_supported(a->C, a->Cout, a->dg), "dcn_v2_fused_tc: C=%d dg=%d unsupported", a->C, a->dg);
-    C2M_CHECK_ARG(a->xs_c == 1, "dcn_v2_fused_tc: input must be channels-last (channel stride 1, got %lld)", a->xs_c);
-    C2M_CHECK_ARG((a->xs_x % 4) == 0 && (a->xs_y % 4) == 0 && (a->xs_b % 4) == 0 && ((uintptr_t)a->x % 16) == 0,
-                  "dcn_v2_fused_tc: input rows must be 16-byte aligned");
     C2M_CHECK_ARG(!(a->pre == nullptr && a->idx != nullptr) || (a->gh > 0 && a->gw > 0 && a->ref_gw > 0 && a->pre_scale > 0),
                   "dcn_v2_fused_tc: idx given without a valid grid/scale");
     C2M_CHECK_ARG((a->out_hi == nullptr) == (a->out_lo == nullptr) && (a->out_hi || a->out_f32), "dcn_v2_fused_tc: bad outputs");
@@ -451,7 +456,8 @@ extern "C" int c2m_dcn_v2_fused_tc(const c2m_dcn_tc_args *a, c2m_stream_t stream
     q.out_hi = reinterpret_cast<__half *>(a->out_hi); q.out_lo = reinterpret_cast<__half *>(a->out_lo);
     q.out_f32 = a->out_f32;
     DcnTc d;
-    d.x = a->x; d.xs_b = a->xs_b; d.xs_c = a->xs_c; d.xs_y = a->xs_y; d.xs_x = a->xs_x;
+    d.x_hi = reinterpret_cast<const __half *>(a->x_hi); d.x_lo = reinterpret_cast<const __half *>(a->x_lo);
+    d.C8 = a->C / 8;
     d.om = a->om; d.pre = a->pre; d.idx = reinterpret_cast<const long long *>(a->idx);
     d.gh = a->gh; d.gw = a->gw; d.ref_gw = a->ref_gw; d.pre_scale = a->pre_scale;
     d.C = a->C; d.dg = a->dg; d.cpg = a->C / a->dg; d.opp = d.cpg / 8; d.n_ko = (a->C / 8) * 9;

@@ -147,12 +147,13 @@ int c2m_psa_maxpool2(const void *hi, const void *lo, int B, int C, int H, int W,
 /* --- DCNv2 forward on tcgen05 (3x3 / stride 1 / pad 1 / dilation 1, C/dg % 8 == 0, Cout <= 256) ---
  * Same contract as c2m_dcn_v2_fused_forward_f32 (raw conv_offset_mask output `om`, pre-offsets from
  * `pre` or rebuilt from `idx`), but the contraction runs as a split-fp16 tensor-core GEMM fed by
- * gather warps; the input must be channels-last (xs_c == 1).  Outputs: PSA (out_hi/out_lo) and / or
+ * gather warps; the input is a PSA tensor (x_hi / x_lo, see c2m_psa_from_f32): its octet-planar layout
+ * lets a warp's corner fetches share cache lines.  Outputs: PSA (out_hi/out_lo) and / or
  * strided fp32; `lrelu` != 0 applies LeakyReLU(0.1).  Weights are packed once with
  * c2m_dcn_tc_pack_weights_f32 into c2m_dcn_tc_packed_weight_bytes(C, Cout, dg) bytes.
  */
 typedef struct {
-    const float *x; long long xs_b, xs_c, xs_y, xs_x;
+    const void *x_hi, *x_lo;
     const float *om; const float *pre; const int64_t *idx;
     int gh, gw, ref_gw, pre_scale;
     int B, C, H, W, Cout, dg;

@@ -305,6 +305,7 @@ def dcntc_diag():
             sc = H // 160
             idx = torch.randint(0, gh * gw, (B, gh, gw), device=dev)
             x = torch.randn(B, C, H, H, device=dev).contiguous(memory_format=torch.channels_last)
+            xpsa = ops.psa_from_f32(x)
             om = torch.randn(B, 216, H, H, device=dev)
             wgt = torch.randn(C, C, 3, 3, device=dev) * 0.05
             bias = torch.randn(C, device=dev)
@@ -320,7 +321,7 @@ def dcntc_diag():
                 e1.record()
                 torch.cuda.synchronize()
                 return e0.elapsed_time(e1) / n
-            ms_tc = t(lambda: ops.dcn_v2_fused_tc(x, om, wgt, bias, 8, idx=idx, pre_scale=sc, lrelu=True, psa_out=True, out_f32=False))
+            ms_tc = t(lambda: ops.dcn_v2_fused_tc(xpsa, om, wgt, bias, 8, idx=idx, pre_scale=sc, lrelu=True, psa_out=True, out_f32=False))
             ms_ff = t(lambda: c2m.dcn_v2_fused_forward(x, om, wgt, bias, 8, idx=idx, pre_scale=sc, lrelu_slope=0.1), 3)
             print(f'C={C} H={H}: tc {ms_tc:.3f} ms, ffma {ms_ff:.3f} ms', flush=True)
         except Exception:
