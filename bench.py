@@ -237,14 +237,18 @@ def run_ours(args, rank, world, local_rank):
         r = prof[dom]
         name = {'corr_search': 'corr_umma_kernel', 'conv3x3': 'conv3x3_umma_kernel', 'dcn': 'dcn_umma_kernel'}[dom]
         achieved = r['flops'] / (r['ms'] / 1e3) / 1e12
-        traffic = None
+        traffic, traffic_shape = None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'dominant_kernel_traffic.json'))).get(name)
+            tj = json.load(open(os.path.join(ROOT, 'profiles', 'dominant_kernel_traffic.json')))
+            traffic = tj.get(name)                      # ncu dram read+write per launch (null if shapes vary)
+            if (tj.get('dominant_shape') or {}).get('kernel') == name:
+                traffic_shape = tj['dominant_shape']
         except Exception:
             pass
         issued = {'conv3x3': 3.0, 'corr_search': 3.0, 'dcn': 3.0}[dom]
         roofline = {'bound': 'tensor', 'kernel': name, 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
-                    'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+                    'frac': achieved / peak, 'traffic': traffic, 'traffic_dominant_shape': traffic_shape,
+                    'peak_source': peak_src,
                     'ms_per_launch': r['ms'] / r['launches'], 'launches_timed': r['launches'],
                     'algorithmic_flops_per_launch': r['flops'] / r['launches'],
                     'algorithmic_bytes_per_launch': r['bytes'] / r['launches'],

@@ -93,6 +93,8 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_p;
     const int sw = *reinterpret_cast<const int *>(q.wblob);              // weight scale exponent
+    // all weight chunks of the (single) slice fit the chunk slots: load them once per CTA, not per item
+    const bool w_resident = p.nslice == 1 && p.nkc <= NBST;
 
     // item -> (b, st, slice): slice fastest so concurrently running CTAs share activation tiles in L2
     auto decode = [&](int item, int &b, int &t0, int &nt, int &slice) {
@@ -137,6 +139,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 int b, t0, nt, slice;
                 decode(item, b, t0, nt, slice);
+                if (w_resident && item != (int)blockIdx.x) break;
                 for (int kc = 0; kc < p.nkc; ++kc) {
                     mbar_wait(&bempty[bst], bphase ^ 1);
                     mbar_arrive_expect_tx(&bfull[bst], w_chunk);
@@ -166,9 +169,12 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 int b, t0, nt, slice;
                 decode(item, b, t0, nt, slice);
+                const bool first_item = item == (int)blockIdx.x;
                 for (int kc = 0; kc < p.nkc; ++kc) {
-                    mbar_wait(&bfull[bst], bphase);
-                    tc_fence_after();
+                    if (!w_resident || first_item) {
+                        mbar_wait(&bfull[bst], bphase);
+                        tc_fence_after();
+                    }
                     const uint32_t w_st = smem_u32(sW + bst * w_chunk);
                     for (int t = 0; t < nt; ++t) {
                         if (kc == 0) {
@@ -199,9 +205,10 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                         if (kc == p.nkc - 1) { umma_commit(&tfull[t]); tph ^= 1u << t; }
                     }
-                    umma_commit(&bempty[bst]);
+                    if (!w_resident) umma_commit(&bempty[bst]);
                     if (++bst == NBST) { bst = 0; bphase ^= 1; }
                 }
+                if (w_resident) { bst = 0; }          // chunk kc always lives in slot kc
             }
         }
     } else if (warp >= 4) {
