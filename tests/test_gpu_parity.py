@@ -518,3 +518,44 @@ def test_psa_maxpool_and_vgg_trunk_fast_path():
                 slow[name] = xn
     for k in slow:
         _rel_ok(fast[k], slow[k], 2e-5)
+
+
+# ------------------------------------------------------------------------------- full-size properties
+def test_dcn_full_size_reduces_to_plain_conv():
+    """BASELINE config 2 large layer (64 ch, 640x640): with zero learned offsets, an identity index
+    map (zero flow) and zero mask logits the deformable conv must equal 0.5 * conv3x3(x, W) + bias."""
+    from c2m_b200 import ops
+    C, H, dg, gh = 64, 640, 8, 158
+    x = seeding.randn(81, (1, C, H, H)).to(DEV)
+    w = seeding.randn(82, (C, C, 3, 3), 0.05).to(DEV)
+    b = seeding.randn(83, (C,)).to(DEV)
+    om = torch.zeros(1, 27 * dg, H, H, device=DEV)
+    idx = torch.arange(gh * gh, device=DEV, dtype=torch.int64).view(1, gh, gh)
+    got = ops.dcn_v2_fused_tc(x, om, w, b, dg, idx=idx, pre_scale=4, lrelu=False)
+    want = 0.5 * F.conv2d(x, w, None, 1, 1) + b.view(1, -1, 1, 1)
+    _rel_ok(got, want, 1e-4)
+
+
+def test_conv_full_size_vs_cudnn_fp32():
+    from c2m_b200 import ops
+    x = seeding.randn(84, (1, 64, 640, 640)).to(DEV)
+    w = seeding.randn(85, (64, 64, 3, 3), 0.05).to(DEV)
+    b = seeding.randn(86, (64,)).to(DEV)
+    got = ops.psa_to_f32(ops.conv3x3_psa(ops.psa_from_f32(x), w, b, act='relu'))
+    want = F.relu(F.conv2d(x, w, b, 1, 1))
+    _rel_ok(got, want, 1e-4)
+
+
+def test_full_size_pipeline_is_deterministic_and_batch_invariant():
+    """Config-2 shapes (LR 160, Ref 500 -> 640): two runs are bitwise identical (no atomics on the
+    forward path) and image 0 of a B=2 batch equals the B=1 result (index map exactly)."""
+    from c2m_b200.pipeline import RestorationPipeline, synthetic_pair
+    pipe = RestorationPipeline(DEV).load_state_dicts(*_weights()).place()
+    lq, up, ref = [t.to(DEV) for t in synthetic_pair(77, 2, 160, 500)]
+    sr_a, idx_a = pipe.forward(lq, up, ref, return_idx=True)
+    sr_b, idx_b = pipe.forward(lq, up, ref, return_idx=True)
+    assert torch.equal(idx_a, idx_b) and torch.equal(sr_a, sr_b)
+    sr_1, idx_1 = pipe.forward(lq[:1], up[:1], ref[:1], return_idx=True)
+    assert torch.equal(idx_1[0], idx_a[0])
+    _rel_ok(sr_1[0], sr_a[0], 1e-5)
+    assert tuple(sr_a.shape) == (2, 3, 640, 640) and torch.isfinite(sr_a).all()
