@@ -152,13 +152,20 @@ def run_ours(args, rank, world, local_rank):
     from c2m_b200.dist import max_over_ranks
     from c2m_b200.pipeline import RestorationPipeline, synthetic_pair
     import __graft_entry__ as entry
-    entry.build()
 
     dev = torch.device('cuda', local_rank)
     torch.cuda.set_device(dev)
     dist_on = world > 1
     if dist_on:
         torch.distributed.init_process_group('nccl', device_id=dev)
+        # one rank per node (re)builds the native library if it is stale; the others wait
+        if local_rank == 0:
+            entry.build()
+        torch.distributed.barrier()
+        if local_rank != 0:
+            entry.build()
+    else:
+        entry.build()
     pipe = RestorationPipeline(dev, allow_tf32=bool(args.tf32), channels_last=bool(args.channels_last))
     pipe.load_state_dicts(*seeded_weights()).place()
 
