@@ -109,7 +109,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
     if (warp == 0) {
         // ================================ activation producer ===============================
         if (lane == 0) {
-            int stage = 0, phase = 0;
+            int stage = 0, phase = 0, n_issued = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 int b, t0, nt, slice;
                 decode(item, b, t0, nt, slice);
@@ -122,9 +122,14 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                         const int y0 = (tt / p.tiles_x) * T_R, x0 = (tt % p.tiles_x) * T_C;
                         mbar_wait(&empty[stage], phase ^ 1);
                         uint8_t *s = sA + stage * A_STAGE;
-                        mbar_arrive_expect_tx(&full[stage], A_STAGE);
-                        tma_load_4d(s, mh, &full[stage], (x0 - 1) * 8, y0 - 1, oct0, b);
-                        tma_load_4d(s + A_HALF, ml, &full[stage], (x0 - 1) * 8, y0 - 1, oct0, b);
+                        if ((p.dbg & 2) && n_issued >= NSTAGE) {
+                            mbar_arrive(&full[stage]);                 // experiment: reuse stale tiles
+                        } else {
+                            mbar_arrive_expect_tx(&full[stage], A_STAGE);
+                            tma_load_4d(s, mh, &full[stage], (x0 - 1) * 8, y0 - 1, oct0, b);
+                            tma_load_4d(s + A_HALF, ml, &full[stage], (x0 - 1) * 8, y0 - 1, oct0, b);
+                        }
+                        ++n_issued;
                         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -532,6 +537,8 @@ extern "C" int c2m_conv3x3(const c2m_conv3x3_args *a, c2m_stream_t stream) {
         if (t >= 1 && t < p.T) p.T = t;
     }
     p.stacked = 1;
+    p.dbg = 0;
+    if (const char *ev = getenv("C2M_CONV_DBG")) p.dbg = atoi(ev);
     p.n_st = ceil_div(p.tiles_x * p.tiles_y, p.T);
     p.act = a->act; p.sa_in = a->sa_in; p.sa_res = a->sa_res; p.sa_out = a->sa_out;
     p.ps = a->pixel_shuffle;

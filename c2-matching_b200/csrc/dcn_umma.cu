@@ -448,6 +448,7 @@ extern "C" int c2m_dcn_v2_fused_tc(const c2m_dcn_tc_args *a, c2m_stream_t stream
     p.sa_in = 0; p.sa_res = 0; p.sa_out = a->sa_out;
     p.ps = 0;
     p.stacked = 0;
+    p.dbg = 0;
     p.C8out = (a->Cout + 7) / 8; p.Hout = a->H; p.Wout = a->W;
     p.os_b = a->os_b; p.os_c = a->os_c; p.os_y = a->os_y; p.os_x = a->os_x;
     ConvPtrs q = {};

@@ -18,6 +18,7 @@ struct ConvParams {
     int sa_in, sa_res, sa_out;
     int ps;                   // 0 or 2: PixelShuffle(2) applied to the PSA output
     int stacked;              // 1: accumulator has 2N columns, value = col[c] + col[N + c]
+    int dbg;                  // tuning experiments only (C2M_CONV_DBG): 1 = no global stores, 2 = no TMA reloads
     int C8out, Hout, Wout;    // geometry of the PSA output tensor
     long long os_b, os_c, os_y, os_x;   // fp32 output element strides
 };
@@ -98,7 +99,7 @@ __device__ __forceinline__ void epilogue_store_block(const ConvPtrs &q, const Co
                         } else {
                             tmem_ld_wait();
                         }
-                        if (!ok) return;
+                        if (!ok || (p.dbg & 1)) return;
                         const int ncol = min(32, p.N - c0);
                         float v[32];
     #pragma unroll
