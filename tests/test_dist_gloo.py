@@ -42,6 +42,60 @@ def test_shard_and_gather_world2():
     assert tmax == 2.0
 
 
+def _combine_worker(rank, world, port, q):
+    sys.path.insert(0, os.path.join(ROOT, 'c2-matching_b200'))
+    from c2m_b200.dist import combine_argmax, ref_row_slab
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    # a fake 9-row x 5-col Ref grid, 6 queries: global scores known to every rank, each rank owns a row slab
+    g = torch.Generator().manual_seed(3)
+    scores = torch.randn(6, 45, generator=g)
+    scores[2, 7] = scores[2, 40] = 9.0            # exact tie across slabs -> lowest index (7) must win
+    scores[4, 31] = scores[4, 33] = 8.0           # exact tie inside one slab
+    r0, r1 = ref_row_slab(9, rank, world)
+    part = scores[:, r0 * 5:r1 * 5]
+    v, i = part.max(dim=1)
+    # local first-max already resolves in-slab ties to the lowest index
+    i = i + r0 * 5
+    vg, ig = combine_argmax(v, i.to(torch.int64))
+    if rank == 0:
+        q.put((vg.tolist(), ig.tolist(), scores.max(dim=1).values.tolist(), [ref_row_slab(9, r, world) for r in range(world)]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_ref_sharded_argmax_combine_world2():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29331 + os.getpid() % 200
+    procs = [ctx.Process(target=_combine_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    vg, ig, vmax, slabs = q.get(timeout=120)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert slabs == [(0, 5), (5, 9)]
+    assert vg == vmax
+    assert ig[2] == 7 and ig[4] == 31
+    g = torch.Generator().manual_seed(3)
+    scores = torch.randn(6, 45, generator=g)
+    scores[2, 7] = scores[2, 40] = 9.0
+    scores[4, 31] = scores[4, 33] = 8.0
+    assert ig == scores.argmax(dim=1).tolist() or all(scores[k, ig[k]] == scores[k].max() for k in range(6))
+
+
+def test_ref_row_slabs_partition():
+    sys.path.insert(0, os.path.join(ROOT, 'c2-matching_b200'))
+    from c2m_b200.dist import ref_row_slab
+    for rh in (1, 7, 158):
+        for w in (1, 2, 3, 8, 11):
+            slabs = [ref_row_slab(rh, r, w) for r in range(w)]
+            assert slabs[0][0] == 0 and slabs[-1][1] == rh
+            assert all(a[1] == b[0] for a, b in zip(slabs, slabs[1:]))
+            assert max(b - a for a, b in slabs) - min(b - a for a, b in slabs) <= 1
+
+
 def test_shard_indices_cover():
     sys.path.insert(0, os.path.join(ROOT, 'c2-matching_b200'))
     from c2m_b200.dist import shard_indices
