@@ -73,10 +73,8 @@ def corr_argmax_ref_sharded(feat_in, feat_ref, patch_size=3, is_norm=True, norm_
     rh, rw = hr - patch_size + 1, wr - patch_size + 1
     r0, r1 = ref_row_slab(rh, rank, world)
     if l2norm:          # normalise per pixel BEFORE slicing so every rank sees the same values
-        c = feat_ref.shape[1]
         feat_ref = torch.nn.functional.normalize(feat_ref, dim=1)
         feat_in = torch.nn.functional.normalize(feat_in, dim=1)
-        del c
     if r1 > r0:
         slab = feat_ref[:, :, r0:r1 + patch_size - 1].contiguous()
         idx, val = ops.corr_argmax(feat_in, slab, patch_size, 1, 1, is_norm, norm_input)
