@@ -559,3 +559,25 @@ def test_full_size_pipeline_is_deterministic_and_batch_invariant():
     assert torch.equal(idx_1[0], idx_a[0])
     _rel_ok(sr_1[0], sr_a[0], 1e-5)
     assert tuple(sr_a.shape) == (2, 3, 640, 640) and torch.isfinite(sr_a).all()
+
+
+def test_non_square_pipeline_fast_vs_module_path(monkeypatch):
+    """CUFED5-like non-square pair (LR 84x124 -> 336x496, Ref 300x420 zero-padded): tcgen05 conv/DCN
+    path vs the cuDNN + FFMA module path give the same index map and SR (ragged tiles on every scale)."""
+    from c2m_b200.pipeline import RestorationPipeline
+    pipe = RestorationPipeline(DEV).load_state_dicts(*_weights()).place()
+    g = torch.Generator().manual_seed(5)
+    lr_h, lr_w = 84, 124
+    lq = torch.rand(1, 3, lr_h, lr_w, generator=g)
+    up = F.interpolate(lq, scale_factor=4, mode='bicubic', align_corners=False).clamp(0, 1)
+    ref = F.pad(torch.rand(1, 3, 300, 420, generator=g), (0, 4 * lr_w - 420, 0, 4 * lr_h - 300))
+    args = [t.to(DEV) for t in (lq, up, ref)]
+    sr_fast, idx_fast = pipe.forward(*args, return_idx=True)
+    monkeypatch.setenv('C2M_FAST_CONV', '0')
+    monkeypatch.setenv('C2M_DCN_TC', '0')
+    sr_slow, idx_slow = pipe.forward(*args, return_idx=True)
+    assert tuple(sr_fast.shape) == (1, 3, 4 * lr_h, 4 * lr_w)
+    flips = int((idx_fast != idx_slow).sum())
+    assert flips <= 3, flips
+    if flips == 0:
+        _rel_ok(sr_fast, sr_slow, 1e-3)
