@@ -45,8 +45,19 @@ struct DcnTc {
     int gh, gw, ref_gw, pre_scale;
     int C, dg, cpg, opp;       // opp = octets per (g, tap) pair = cpg / 8
     int n_ko;                  // real K octets = C/8 * 9
+    int opp_shift;             // log2(opp): octets per (g,tap) pair is 1, 2 or 4 for C/dg in {8,16,32}; -1 otherwise
+    float inv_ref_gw, inv_scale;   // reciprocals for the exact float-assisted integer divisions
 };
 }  // namespace
+
+// exact n / d for 0 <= n < 2^23 with a precomputed float reciprocal (one multiply + fix-up instead
+// of the ~25-instruction integer division sequence; the gather loop is issue-bound)
+__device__ __forceinline__ int fast_div(int n, int d, float inv_d) {
+    int q = (int)((float)n * inv_d);
+    const int r = n - q * d;
+    q += (r >= d) - (r < 0);
+    return q;
+}
 
 __global__ void __launch_bounds__(512, 1)
 dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
@@ -203,36 +214,43 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
             decode(item, b, t0, nt, slice);
             const __half *xh = d.x_hi + (size_t)b * d.C8 * p.H * p.W * 8;
             const __half *xl = d.x_lo + (size_t)b * d.C8 * p.H * p.W * 8;
-            const float *omb = d.om + (long long)b * 3 * d.dg * 9 * P;
+            const float *omb = d.om + (size_t)b * 3 * d.dg * 9 * P;
             const long long *idxb = d.idx ? d.idx + (long long)b * d.gh * d.gw : nullptr;
             const float *preb = d.pre ? d.pre + (long long)b * 9 * P * 2 : nullptr;
             const int n_steps = p.nkc * nt;
 
-            // metadata fetch for (step, u): raw offsets + mask logit + index-map entry
-            auto fetch = [&](int step, int u, Meta &mt, int &pair_out, bool &live) {
-                const int kc = step / nt, t = step - kc * nt;
+            // (kc, t) and the pixel of this thread in tile t are advanced incrementally; all divisions by
+            // run-time values go through fast_div / shifts
+            const int mrow = m / T_C, mcol = m % T_C;
+            const float inv_tx = 1.f / (float)p.tiles_x;
+            const int opp_shift = d.opp_shift;
+            const int om_mask_base = 2 * d.dg * 9;
+
+            // metadata fetch for (kc, t, u): raw offsets + mask logit + index-map entry
+            auto fetch = [&](int kc, int t, bool in_range, int u, Meta &mt, int &pair_out, bool &live) {
                 const int tt = t0 + t;
-                const int y = (tt / p.tiles_x) * T_R + m / T_C, xx = (tt % p.tiles_x) * T_C + m % T_C;
+                const int ty = fast_div(tt, p.tiles_x, inv_tx);
+                const int y = ty * T_R + mrow, xx = (tt - ty * p.tiles_x) * T_C + mcol;
                 const int ko = kc * KOCT + oh * 2 + u;
-                live = step < n_steps && y < p.H && xx < p.W && ko < d.n_ko;
-                pair_out = ko / d.opp;
+                live = in_range && y < p.H && xx < p.W && ko < d.n_ko;
+                pair_out = opp_shift >= 0 ? (ko >> opp_shift) : ko / d.opp;
                 mt.off_h = mt.off_w = mt.mr = 0.f;
                 mt.v = -1;
                 if (!live) return;
                 const int g = pair_out / 9, tap = pair_out - g * 9;
                 const int jj = g * 9 + tap, pp = y * p.W + xx;
-                mt.off_h = omb[(long long)(2 * jj) * P + pp];
-                mt.off_w = omb[(long long)(2 * jj + 1) * P + pp];
-                mt.mr = omb[(long long)(2 * d.dg * 9 + jj) * P + pp];
+                mt.off_h = omb[(2 * jj) * P + pp];
+                mt.off_w = omb[(2 * jj + 1) * P + pp];
+                mt.mr = omb[(om_mask_base + jj) * P + pp];
                 if (preb) {
-                    const float2 pq = *reinterpret_cast<const float2 *>(preb + ((long long)tap * P + pp) * 2);
+                    const float2 pq = *reinterpret_cast<const float2 *>(preb + ((size_t)tap * P + pp) * 2);
                     mt.off_w += pq.x;
                     mt.off_h += pq.y;
                 } else if (idxb) {
                     const int sc = d.pre_scale, ki = tap / 3, kj = tap - ki * 3;
                     const int ys = y - sc * ki, xs = xx - sc * kj;
                     if (ys >= 0 && xs >= 0) {
-                        const int yy = ys / sc, xg = xs / sc;
+                        const int yy = fast_div(ys, sc, d.inv_scale), xg = fast_div(xs, sc, d.inv_scale);
                         if (yy < d.gh && xg < d.gw) mt.v = (int)idxb[yy * d.gw + xg];
                     }
                 }
@@ -241,12 +259,16 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
             Meta mt[2], nx[2];
             int pr[2], npr[2];
             bool lv[2], nlv[2];
-            fetch(0, 0, mt[0], pr[0], lv[0]);
-            fetch(0, 1, mt[1], pr[1], lv[1]);
+            fetch(0, 0, n_steps > 0, 0, mt[0], pr[0], lv[0]);
+            fetch(0, 0, n_steps > 0, 1, mt[1], pr[1], lv[1]);
+            int kc = 0, t = 0;
             for (int step = 0; step < n_steps; ++step) {
-                const int kc = step / nt, t = step - kc * nt;
                 const int tt = t0 + t;
-                const int y = (tt / p.tiles_x) * T_R + m / T_C, xx = (tt % p.tiles_x) * T_C + m % T_C;
+                const int ty = fast_div(tt, p.tiles_x, inv_tx);
+                const int y = ty * T_R + mrow, xx = (tt - ty * p.tiles_x) * T_C + mcol;
+                // next (kc, t)
+                int nkc_ = kc, nt_ = t + 1;
+                if (nt_ == nt) { nt_ = 0; ++nkc_; }
                 // ---- sampling points of the two octets
                 int o[2][4];
                 float wq[2][4], mk[2];
@@ -260,8 +282,8 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
                         float off_h = mt[u].off_h, off_w = mt[u].off_w;
                         if (mt[u].v >= 0) {
                             const int sc = d.pre_scale;
-                            const int yy = (y - sc * ki) / sc, xg = (xx - sc * kj) / sc;
-                            const int vy = mt[u].v / d.ref_gw, vx = mt[u].v - vy * d.ref_gw;
+                            const int yy = fast_div(y - sc * ki, sc, d.inv_scale), xg = fast_div(xx - sc * kj, sc, d.inv_scale);
+                            const int vy = fast_div(mt[u].v, d.ref_gw, d.inv_ref_gw), vx = mt[u].v - vy * d.ref_gw;
                             off_w += (float)(sc * (vx - xg));
                             off_h += (float)(sc * (vy - yy));
                         }
@@ -274,17 +296,18 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
                             const float hh = 1.f - lh, hw = 1.f - lw;
                             const bool tv = h_low >= 0, bv = h_high <= p.H - 1, lvv = w_low >= 0, rv = w_high <= p.W - 1;
                             // channel octet of this K octet, as an element offset of its [H][W][8] plane
-                            const int oct_c = g * (d.cpg / 8) + (oh * 2 + u + kc * KOCT - pr[u] * d.opp);
-                            const int cbase = oct_c * p.H * p.W * 8;
-                            if (tv && lvv) { o[u][0] = (h_low * p.W + w_low) * 8 + cbase; wq[u][0] = hh * hw; }
-                            if (tv && rv) { o[u][1] = (h_low * p.W + w_high) * 8 + cbase; wq[u][1] = hh * lw; }
-                            if (bv && lvv) { o[u][2] = (h_high * p.W + w_low) * 8 + cbase; wq[u][2] = lh * hw; }
-                            if (bv && rv) { o[u][3] = (h_high * p.W + w_high) * 8 + cbase; wq[u][3] = lh * lw; }
+                            const int ko = kc * KOCT + oh * 2 + u;
+                            const int oct_c = g * (d.cpg / 8) + (ko - (opp_shift >= 0 ? (pr[u] << opp_shift) : pr[u] * d.opp));
+                            const int cbase = oct_c * P * 8;
+                            const int r0 = (h_low * p.W + w_low) * 8 + cbase;
+                            if (tv && lvv) { o[u][0] = r0; wq[u][0] = hh * hw; }
+                            if (tv && rv) { o[u][1] = r0 + 8; wq[u][1] = hh * lw; }
+                            if (bv && lvv) { o[u][2] = r0 + p.W * 8; wq[u][2] = lh * hw; }
+                            if (bv && rv) { o[u][3] = r0 + p.W * 8 + 8; wq[u][3] = lh * lw; }
                             mk[u] = 1.f / (1.f + expf(-mt[u].mr));
                         }
                     }
                 }
-                // ---- corner fetches of both octets in flight together, then the next stage's metadata
                 // octet-planar operand: the 32 lanes of a warp (4 rows x 8 pixels) read 16 B each from runs of
                 // adjacent pixels (8 lines per request instead of 32 with a channels-last fp32 input)
                 uint4 ch[2][4], cl[2][4];
@@ -295,8 +318,8 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
                         ch[u][c] = *reinterpret_cast<const uint4 *>(xh + o[u][c]);
                         cl[u][c] = *reinterpret_cast<const uint4 *>(xl + o[u][c]);
                     }
-                fetch(step + 1, 0, nx[0], npr[0], nlv[0]);
-                fetch(step + 1, 1, nx[1], npr[1], nlv[1]);
+                fetch(nkc_, nt_, step + 1 < n_steps, 0, nx[0], npr[0], nlv[0]);
+                fetch(nkc_, nt_, step + 1 < n_steps, 1, nx[1], npr[1], nlv[1]);
                 // ---- blend, modulate, split
                 uint4 h_out[2], l_out[2];
 #pragma unroll
@@ -337,6 +360,8 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
 #pragma unroll
                 for (int u = 0; u < 2; ++u) { mt[u] = nx[u]; pr[u] = npr[u]; lv[u] = nlv[u]; }
+                kc = nkc_;
+                t = nt_;
             }
         }
     }
@@ -462,6 +487,12 @@ extern "C" int c2m_dcn_v2_fused_tc(const c2m_dcn_tc_args *a, c2m_stream_t stream
     d.om = a->om; d.pre = a->pre; d.idx = reinterpret_cast<const long long *>(a->idx);
     d.gh = a->gh; d.gw = a->gw; d.ref_gw = a->ref_gw; d.pre_scale = a->pre_scale;
     d.C = a->C; d.dg = a->dg; d.cpg = a->C / a->dg; d.opp = d.cpg / 8; d.n_ko = (a->C / 8) * 9;
+    d.opp_shift = d.opp == 1 ? 0 : d.opp == 2 ? 1 : d.opp == 4 ? 2 : d.opp == 8 ? 3 : -1;
+    d.inv_ref_gw = a->ref_gw > 0 ? 1.f / (float)a->ref_gw : 0.f;
+    d.inv_scale = a->pre_scale > 0 ? 1.f / (float)a->pre_scale : 1.f;
+    C2M_CHECK_ARG((long long)a->H * a->W * 27 * a->dg < (1ll << 31) && (long long)a->H * a->W * a->C < (1ll << 31),
+                  "dcn_v2_fused_tc: map too large for 32-bit in-kernel indexing");
+    C2M_CHECK_ARG(a->idx == nullptr || (long long)a->gh * a->gw < (1 << 23), "dcn_v2_fused_tc: index map too large");
     const size_t smem = (size_t)NBST * 2 * KOCT * p.N * 16 + NSTAGE * A_STAGE + 4096;
     C2M_CUDA(cudaFuncSetAttribute(dcn_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 0;
