@@ -16,10 +16,14 @@
 //   are fetched as 16 B (hi) + 16 B (lo) per corner from the octet-planar PSA input, blended in fp32,
 //   multiplied by the mask, split and stored with one 16 B st.shared per half;
 //   fence.proxy.async + mbarrier hand the stage to the MMA-issuing thread.
-//   Weights stream as 8 KB chunks (bulk copy, 4-deep ring), shared by the item's 8 pixel tiles
-//   (8 TMEM accumulators); the epilogue (bias, LeakyReLU, PSA and / or fp32 store) is shared with
-//   the plain convolution.
+//   Weights stream as 8 KB chunks (bulk copy, 4-deep ring), shared by a group of up to 8 pixel
+//   tiles (512/N TMEM accumulators, rotated across groups); every CTA owns an evenly sized contiguous
+//   range of the flat (slice, image, tile) list, so small problems (BASELINE config 4: 200 tiles)
+//   spread over all SMs.  The epilogue (bias, LeakyReLU, PSA and / or fp32 store) is shared with
+//   the plain convolution.  -DC2M_DCN_TRACE prints a %globaltimer trace of CTA 0's pipeline.
 // The im2col matrix never exists outside shared memory.
+#include <cstdlib>
+
 #include "umma_conv_common.cuh"
 
 namespace c2m {
@@ -59,6 +63,14 @@ __device__ __forceinline__ int fast_div(int n, int d, float inv_d) {
     return q;
 }
 
+#ifdef C2M_DCN_TRACE
+__device__ unsigned long long g_tr[32][4], g_tm[32][3], g_t0[2];
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define TR(x) x
+#else
+#define TR(x)
+#endif
+
 __global__ void __launch_bounds__(512, 1)
 dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -74,8 +86,15 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
     float *sbias = reinterpret_cast<float *>(tmem_base_p + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    TR(if (blockIdx.x == 0 && threadIdx.x == 0) g_t0[0] = gtime();)
     const int tiles_img = p.tiles_x * p.tiles_y;
-    const int n_items = p.B * p.n_st * p.nslice;
+    // Work = flat list of (Cout slice, image, pixel tile); every CTA owns one contiguous, evenly sized range
+    // of it and walks the range in groups of <= T tiles that share the streamed weight chunks.
+    const int TT = p.B * tiles_img;
+    const int n_work = p.nslice * TT;
+    const int w_begin = (int)((long long)n_work * blockIdx.x / gridDim.x);
+    const int w_end = (int)((long long)n_work * (blockIdx.x + 1) / gridDim.x);
+    const int nacc = p.T;                                // TMEM accumulators, rotated across groups
     const uint32_t need_cols = (uint32_t)p.N * p.T;
     const uint32_t tmem_cols = need_cols <= 32 ? 32 : need_cols <= 64 ? 64 : need_cols <= 128 ? 128
                                : need_cols <= 256 ? 256 : 512;
@@ -94,24 +113,22 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_p;
+    TR(if (blockIdx.x == 0 && threadIdx.x == 0) g_t0[1] = gtime();)
+    TR(int trs = 0;)
     const int sw = *reinterpret_cast<const int *>(q.wblob);
 
-    auto decode = [&](int item, int &b, int &t0, int &nt, int &slice) {
-        slice = item % p.nslice;
-        const int r = item / p.nslice;
-        const int st = r % p.n_st;
-        b = r / p.n_st;
-        t0 = st * p.T;
-        nt = min(p.T, tiles_img - t0);
+    auto group = [&](int pos, int &slice, int &nt) {
+        slice = pos / TT;
+        nt = min(min(p.T, w_end - pos), (slice + 1) * TT - pos);
     };
 
     if (warp == 0) {
         // ================================ weight producer ===================================
         if (lane == 0) {
             int bst = 0, bphase = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                int b, t0, nt, slice;
-                decode(item, b, t0, nt, slice);
+            for (int pos = w_begin, nt = 0; pos < w_end; pos += nt) {
+                int slice;
+                group(pos, slice, nt);
                 for (int kc = 0; kc < p.nkc; ++kc) {
                     mbar_wait(&bempty[bst], bphase ^ 1);
                     mbar_arrive_expect_tx(&bfull[bst], w_chunk);
@@ -131,21 +148,26 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
             const uint32_t b_lbo = p.N * 16;
             int stage = 0, phase = 0, bst = 0, bphase = 0;
             uint32_t tph = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                int b, t0, nt, slice;
-                decode(item, b, t0, nt, slice);
+            int abase = 0;
+            for (int pos = w_begin, nt = 0; pos < w_end; pos += nt) {
+                int slice;
+                group(pos, slice, nt);
                 for (int kc = 0; kc < p.nkc; ++kc) {
                     mbar_wait(&bfull[bst], bphase);
                     tc_fence_after();
+                    TR(if (blockIdx.x == 0 && trs < 32) g_tm[trs][0] = gtime();)
                     const uint32_t w_hi = smem_u32(sW + bst * w_chunk), w_lo = w_hi + w_half;
                     for (int t = 0; t < nt; ++t) {
+                        int a = abase + t;
+                        if (a >= nacc) a -= nacc;
                         if (kc == 0) {
-                            mbar_wait(&tempty[t], ((tph >> t) & 1u) ^ 1u);
+                            mbar_wait(&tempty[a], ((tph >> a) & 1u) ^ 1u);
                             tc_fence_after();
                         }
-                        const uint32_t dacc = tmem_base + t * p.N;
+                        const uint32_t dacc = tmem_base + a * p.N;
                         mbar_wait(&full[stage], phase);
                         tc_fence_after();
+                        TR(if (blockIdx.x == 0 && trs < 32) g_tm[trs][1] = gtime();)
                         const uint32_t a_hi = smem_u32(sA + stage * A_STAGE), a_lo = a_hi + A_HALF;
 #pragma unroll
                         for (int j = 0; j < KOCT / 2; ++j) {
@@ -159,12 +181,15 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
                             umma_f16(dacc, dal, dbh, idesc, 1);
                         }
                         umma_commit(&empty[stage]);
+                        TR(if (blockIdx.x == 0 && trs < 32) { g_tm[trs][2] = gtime(); ++trs; })
                         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-                        if (kc == p.nkc - 1) { umma_commit(&tfull[t]); tph ^= 1u << t; }
+                        if (kc == p.nkc - 1) { umma_commit(&tfull[a]); tph ^= 1u << a; }
                     }
                     umma_commit(&bempty[bst]);
                     if (++bst == NBST) { bst = 0; bphase ^= 1; }
                 }
+                abase += nt;
+                if (abase >= nacc) abase -= nacc;
             }
         }
     } else if (warp >= 4 && warp < 8) {
@@ -175,27 +200,36 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
         const float res_scale = 1.f;
         const float so = ldexpf(1.f, p.sa_out);
         uint32_t tph = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            int b, t0, nt, slice;
-            decode(item, b, t0, nt, slice);
+        int abase = 0, cur_slice = -1;
+        for (int pos = w_begin, nt = 0; pos < w_end; pos += nt) {
+            int slice;
+            group(pos, slice, nt);
             const int o_base = slice * p.N;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            for (int i = e; i < p.N; i += 128) sbias[i] = (q.bias && o_base + i < p.Cout) ? q.bias[o_base + i] : 0.f;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (slice != cur_slice) {                      // uniform over the 4 epilogue warps
+                cur_slice = slice;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int i = e; i < p.N; i += 128) sbias[i] = (q.bias && o_base + i < p.Cout) ? q.bias[o_base + i] : 0.f;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
             for (int t = 0; t < nt; ++t) {
-                const int tt = t0 + t;
+                const int r = pos + t - slice * TT;
+                const int b = r / tiles_img, tt = r - b * tiles_img;
                 const int y = (tt / p.tiles_x) * T_R + e / T_C, x = (tt % p.tiles_x) * T_C + e % T_C;
                 const bool ok = y < p.H && x < p.W;
-                mbar_wait(&tfull[t], (tph >> t) & 1u);
-                tph ^= 1u << t;
+                int a = abase + t;
+                if (a >= nacc) a -= nacc;
+                mbar_wait(&tfull[a], (tph >> a) & 1u);
+                tph ^= 1u << a;
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + t * p.N;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * p.N;
                 for (int c0 = 0; c0 < p.N; c0 += 32)
                     epilogue_store_block(q, p, taddr, c0, b, y, x, ok, o_base, sbias, out_scale, res_scale, so);
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[t]);
+                if (lane == 0) mbar_arrive(&tempty[a]);
             }
+            abase += nt;
+            if (abase >= nacc) abase -= nacc;
         }
     } else if (warp >= 8) {
         // ================================ gather producers ==================================
@@ -209,14 +243,12 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
         const int P = p.H * p.W;
         struct Meta { float off_h, off_w, mr; int v; };
         int stage = 0, phase = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            int b, t0, nt, slice;
-            decode(item, b, t0, nt, slice);
-            const __half *xh = d.x_hi + (size_t)b * d.C8 * p.H * p.W * 8;
-            const __half *xl = d.x_lo + (size_t)b * d.C8 * p.H * p.W * 8;
-            const float *omb = d.om + (size_t)b * 3 * d.dg * 9 * P;
-            const long long *idxb = d.idx ? d.idx + (long long)b * d.gh * d.gw : nullptr;
-            const float *preb = d.pre ? d.pre + (long long)b * 9 * P * 2 : nullptr;
+        const float inv_ti = 1.f / (float)tiles_img;
+        const size_t x_img = (size_t)d.C8 * P * 8, om_img = (size_t)3 * d.dg * 9 * P;
+        for (int pos = w_begin, nt = 0; pos < w_end; pos += nt) {
+            int slice;
+            group(pos, slice, nt);
+            const int r0g = pos - slice * TT;               // (image, tile) index of the group's first tile
             const int n_steps = p.nkc * nt;
 
             // (kc, t) and the pixel of this thread in tile t are advanced incrementally; all divisions by
@@ -228,7 +260,9 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
 
             // metadata fetch for (kc, t, u): raw offsets + mask logit + index-map entry
             auto fetch = [&](int kc, int t, bool in_range, int u, Meta &mt, int &pair_out, bool &live) {
-                const int tt = t0 + t;
+                const int b = fast_div(r0g + t, tiles_img, inv_ti);
+                const int tt = r0g + t - b * tiles_img;
+                const float *omb = d.om + b * om_img;
                 const int ty = fast_div(tt, p.tiles_x, inv_tx);
                 const int y = ty * T_R + mrow, xx = (tt - ty * p.tiles_x) * T_C + mcol;
                 const int ko = kc * KOCT + oh * 2 + u;
@@ -242,11 +276,12 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
                 mt.off_h = omb[(2 * jj) * P + pp];
                 mt.off_w = omb[(2 * jj + 1) * P + pp];
                 mt.mr = omb[(om_mask_base + jj) * P + pp];
-                if (preb) {
-                    const float2 pq = *reinterpret_cast<const float2 *>(preb + ((size_t)tap * P + pp) * 2);
+                if (d.pre) {
+                    const float2 pq = *reinterpret_cast<const float2 *>(d.pre + (((size_t)b * 9 + tap) * P + pp) * 2);
                     mt.off_w += pq.x;
                     mt.off_h += pq.y;
-                } else if (idxb) {
+                } else if (d.idx) {
+                    const long long *idxb = d.idx + (long long)b * d.gh * d.gw;
                     const int sc = d.pre_scale, ki = tap / 3, kj = tap - ki * 3;
                     const int ys = y - sc * ki, xs = xx - sc * kj;
                     if (ys >= 0 && xs >= 0) {
@@ -263,7 +298,11 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
             fetch(0, 0, n_steps > 0, 1, mt[1], pr[1], lv[1]);
             int kc = 0, t = 0;
             for (int step = 0; step < n_steps; ++step) {
-                const int tt = t0 + t;
+                const int b = fast_div(r0g + t, tiles_img, inv_ti);
+                const int tt = r0g + t - b * tiles_img;
+                const __half *xh = d.x_hi + b * x_img;
+                const __half *xl = d.x_lo + b * x_img;
+                TR(const bool trc = blockIdx.x == 0 && threadIdx.x == 256 && trs < 32; if (trc) g_tr[trs][0] = gtime();)
                 const int ty = fast_div(tt, p.tiles_x, inv_tx);
                 const int y = ty * T_R + mrow, xx = (tt - ty * p.tiles_x) * T_C + mcol;
                 // next (kc, t)
@@ -346,7 +385,9 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
                     h_out[u] = *reinterpret_cast<const uint4 *>(h8);
                     l_out[u] = *reinterpret_cast<const uint4 *>(l8);
                 }
+                TR(if (trc) g_tr[trs][1] = gtime();)
                 mbar_wait(&empty[stage], phase ^ 1);
+                TR(if (trc) g_tr[trs][2] = gtime();)
                 uint8_t *sdst = sA + stage * A_STAGE;
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
@@ -357,6 +398,7 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full[stage]);
+                TR(if (trc) { g_tr[trs][3] = gtime(); } ++trs;)
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
 #pragma unroll
                 for (int u = 0; u < 2; ++u) { mt[u] = nx[u]; pr[u] = npr[u]; lv[u] = nlv[u]; }
@@ -372,6 +414,13 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
         tc_fence_after();
         tmem_dealloc(tmem_base, tmem_cols);
     }
+    TR(if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const unsigned long long z = g_t0[0];
+        printf("TRACE setup %llu end %llu\n", g_t0[1] - z, gtime() - z);
+        for (int i = 0; i < 24; ++i)
+            printf("  s%02d gather top %6llu loads %6llu wait %6llu arr %6llu | mma bfull %6llu full %6llu commit %6llu\n", i,
+                   g_tr[i][0] - z, g_tr[i][1] - z, g_tr[i][2] - z, g_tr[i][3] - z, g_tm[i][0] - z, g_tm[i][1] - z, g_tm[i][2] - z);
+    })
 }
 
 // blob: header | [slice][kc][hi|lo][octet 4][N][8], K ordered (g, tap, channel-in-group)
@@ -498,13 +547,14 @@ extern "C" int c2m_dcn_v2_fused_tc(const c2m_dcn_tc_args *a, c2m_stream_t stream
     int dev = 0, sms = 0;
     C2M_CUDA(cudaGetDevice(&dev));
     C2M_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int n_items = a->B * p.n_st * p.nslice;
+    const long long n_work = (long long)a->B * p.tiles_x * p.tiles_y * p.nslice;
+    C2M_CHECK_ARG(n_work < (1 << 23), "dcn_v2_fused_tc: too many pixel tiles");
     // flops = 2*B*Cout*C*9*Ho*Wo; bytes = 4*B*(C*H*W + 3*dg*9*H*W + Cout*H*W) + weights
     const double px = (double)a->B * a->H * a->W;
     const double flops = 2.0 * a->Cout * a->C * 9.0 * px;
     const double bytes = 4.0 * px * (a->C + 27.0 * a->dg + a->Cout) + 4.0 * a->Cout * (a->C * 9.0 + 1.0);
     void *ph = prof_begin(PROF_DCN, flops, bytes, st);
-    dcn_umma_kernel<<<n_items < sms ? n_items : sms, 512, smem, st>>>(q, p, d);
+    dcn_umma_kernel<<<n_work < sms ? (int)n_work : sms, 512, smem, st>>>(q, p, d);
     C2M_LAUNCH_CHECK("dcn_umma_kernel");
     prof_end(ph, st);
     return C2M_OK;
