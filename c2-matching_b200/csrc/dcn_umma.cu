@@ -37,7 +37,12 @@ constexpr int A_STAGE = 2 * A_HALF;        // 16384 B
 constexpr int NSTAGE = 4;
 constexpr int NBST = 4;
 constexpr int MAXT = 8;
-constexpr int NGATHER_WARPS = 8;
+#ifndef C2M_DCN_NU
+#define C2M_DCN_NU 1
+#endif
+constexpr int NU = C2M_DCN_NU;                       // K octets per gather thread and stage
+constexpr int NGATHER_WARPS = 4 * KOCT / NU;         // thread = (pixel of the tile, NU octets of the chunk)
+constexpr int NTHREADS = 256 + 32 * NGATHER_WARPS;
 constexpr int W_HDR = 256;
 
 struct DcnTc {
@@ -71,7 +76,7 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 #define TR(x)
 #endif
 
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(NTHREADS, 1)
 dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -122,6 +127,11 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
         nt = min(min(p.T, w_end - pos), (slice + 1) * TT - pos);
     };
 
+    // Register budget per warpgroup.  The CTA's pool is what it was launched with (80 x 768 = 61440):
+    // the control warpgroup gives 40 x 128 back and the epilogue (32 TMEM columns in flight) takes
+    // them, 40 + 120 + 4 x 80 = 480 = 6 x 80.  Requests beyond the pool would block forever.
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == 0) {
         // ================================ weight producer ===================================
         if (lane == 0) {
@@ -192,7 +202,9 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
                 if (abase >= nacc) abase -= nacc;
             }
         }
-    } else if (warp >= 4 && warp < 8) {
+    }
+    } else if (warp < 8) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
         // ================================ epilogue ==========================================
         const int e = threadIdx.x - 128;
         const int quarter = warp & 3;
@@ -231,13 +243,13 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
             abase += nt;
             if (abase >= nacc) abase -= nacc;
         }
-    } else if (warp >= 8) {
+    } else {
         // ================================ gather producers ==================================
         // Thread = (pixel m of the tile, octet pair oh of the chunk).  Per stage two dependent
         // memory round trips exist (offsets/mask/idx -> corner addresses -> corner values); the
         // first one is taken off the critical path by fetching the NEXT stage's metadata while the
         // current stage's corners are in flight.
-        const int g_tid = threadIdx.x - 256;             // 0..255
+        const int g_tid = threadIdx.x - 256;
         const int m = g_tid & 127;
         const int oh = g_tid >> 7;
         const int P = p.H * p.W;
@@ -265,7 +277,7 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
                 const float *omb = d.om + b * om_img;
                 const int ty = fast_div(tt, p.tiles_x, inv_tx);
                 const int y = ty * T_R + mrow, xx = (tt - ty * p.tiles_x) * T_C + mcol;
-                const int ko = kc * KOCT + oh * 2 + u;
+                const int ko = kc * KOCT + oh * NU + u;
                 live = in_range && y < p.H && xx < p.W && ko < d.n_ko;
                 pair_out = opp_shift >= 0 ? (ko >> opp_shift) : ko / d.opp;
                 mt.off_h = mt.off_w = mt.mr = 0.f;
@@ -291,11 +303,11 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
                 }
             };
 
-            Meta mt[2], nx[2];
-            int pr[2], npr[2];
-            bool lv[2], nlv[2];
-            fetch(0, 0, n_steps > 0, 0, mt[0], pr[0], lv[0]);
-            fetch(0, 0, n_steps > 0, 1, mt[1], pr[1], lv[1]);
+            Meta mt[NU], nx[NU];
+            int pr[NU], npr[NU];
+            bool lv[NU], nlv[NU];
+#pragma unroll
+            for (int u = 0; u < NU; ++u) fetch(0, 0, n_steps > 0, u, mt[u], pr[u], lv[u]);
             int kc = 0, t = 0;
             for (int step = 0; step < n_steps; ++step) {
                 const int b = fast_div(r0g + t, tiles_img, inv_ti);
@@ -309,10 +321,10 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
                 int nkc_ = kc, nt_ = t + 1;
                 if (nt_ == nt) { nt_ = 0; ++nkc_; }
                 // ---- sampling points of the two octets
-                int o[2][4];
-                float wq[2][4], mk[2];
+                int o[NU][4];
+                float wq[NU][4], mk[NU];
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
+                for (int u = 0; u < NU; ++u) {
                     o[u][0] = o[u][1] = o[u][2] = o[u][3] = 0;
                     wq[u][0] = wq[u][1] = wq[u][2] = wq[u][3] = 0.f;
                     mk[u] = 0.f;
@@ -335,7 +347,7 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
                             const float hh = 1.f - lh, hw = 1.f - lw;
                             const bool tv = h_low >= 0, bv = h_high <= p.H - 1, lvv = w_low >= 0, rv = w_high <= p.W - 1;
                             // channel octet of this K octet, as an element offset of its [H][W][8] plane
-                            const int ko = kc * KOCT + oh * 2 + u;
+                            const int ko = kc * KOCT + oh * NU + u;
                             const int oct_c = g * (d.cpg / 8) + (ko - (opp_shift >= 0 ? (pr[u] << opp_shift) : pr[u] * d.opp));
                             const int cbase = oct_c * P * 8;
                             const int r0 = (h_low * p.W + w_low) * 8 + cbase;
@@ -349,20 +361,20 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
                 }
                 // octet-planar operand: the 32 lanes of a warp (4 rows x 8 pixels) read 16 B each from runs of
                 // adjacent pixels (8 lines per request instead of 32 with a channels-last fp32 input)
-                uint4 ch[2][4], cl[2][4];
+                uint4 ch[NU][4], cl[NU][4];
 #pragma unroll
-                for (int u = 0; u < 2; ++u)
+                for (int u = 0; u < NU; ++u)
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         ch[u][c] = *reinterpret_cast<const uint4 *>(xh + o[u][c]);
                         cl[u][c] = *reinterpret_cast<const uint4 *>(xl + o[u][c]);
                     }
-                fetch(nkc_, nt_, step + 1 < n_steps, 0, nx[0], npr[0], nlv[0]);
-                fetch(nkc_, nt_, step + 1 < n_steps, 1, nx[1], npr[1], nlv[1]);
-                // ---- blend, modulate, split
-                uint4 h_out[2], l_out[2];
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
+                for (int u = 0; u < NU; ++u) fetch(nkc_, nt_, step + 1 < n_steps, u, nx[u], npr[u], nlv[u]);
+                // ---- blend, modulate, split
+                uint4 h_out[NU], l_out[NU];
+#pragma unroll
+                for (int u = 0; u < NU; ++u) {
                     __align__(16) __half h8[8];
                     __align__(16) __half l8[8];
                     const __half *hp[4], *lp[4];
@@ -390,8 +402,8 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
                 TR(if (trc) g_tr[trs][2] = gtime();)
                 uint8_t *sdst = sA + stage * A_STAGE;
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int oct = oh * 2 + u;
+                for (int u = 0; u < NU; ++u) {
+                    const int oct = oh * NU + u;
                     *reinterpret_cast<uint4 *>(sdst + oct * A_OCT_B + m * 16) = h_out[u];
                     *reinterpret_cast<uint4 *>(sdst + A_HALF + oct * A_OCT_B + m * 16) = l_out[u];
                 }
@@ -401,7 +413,7 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
                 TR(if (trc) { g_tr[trs][3] = gtime(); } ++trs;)
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
 #pragma unroll
-                for (int u = 0; u < 2; ++u) { mt[u] = nx[u]; pr[u] = npr[u]; lv[u] = nlv[u]; }
+                for (int u = 0; u < NU; ++u) { mt[u] = nx[u]; pr[u] = npr[u]; lv[u] = nlv[u]; }
                 kc = nkc_;
                 t = nt_;
             }
@@ -554,7 +566,7 @@ extern "C" int c2m_dcn_v2_fused_tc(const c2m_dcn_tc_args *a, c2m_stream_t stream
     const double flops = 2.0 * a->Cout * a->C * 9.0 * px;
     const double bytes = 4.0 * px * (a->C + 27.0 * a->dg + a->Cout) + 4.0 * a->Cout * (a->C * 9.0 + 1.0);
     void *ph = prof_begin(PROF_DCN, flops, bytes, st);
-    dcn_umma_kernel<<<n_work < sms ? (int)n_work : sms, 512, smem, st>>>(q, p, d);
+    dcn_umma_kernel<<<n_work < sms ? (int)n_work : sms, NTHREADS, smem, st>>>(q, p, d);
     C2M_LAUNCH_CHECK("dcn_umma_kernel");
     prof_end(ph, st);
     return C2M_OK;
