@@ -31,7 +31,7 @@ class ConvArgs(ctypes.Structure):
                 ('pixel_shuffle', ctypes.c_int),
                 ('out_f32', ctypes.c_void_p), ('add_f32', ctypes.c_void_p),
                 ('os_b', ctypes.c_longlong), ('os_c', ctypes.c_longlong), ('os_y', ctypes.c_longlong),
-                ('os_x', ctypes.c_longlong)]
+                ('os_x', ctypes.c_longlong), ('out_f32_octets', ctypes.c_int)]
 
 
 class DcnTcArgs(ctypes.Structure):
@@ -44,7 +44,7 @@ class DcnTcArgs(ctypes.Structure):
                 ('packed_w', ctypes.c_void_p), ('bias', ctypes.c_void_p), ('lrelu', ctypes.c_int),
                 ('out_hi', ctypes.c_void_p), ('out_lo', ctypes.c_void_p), ('sa_out', ctypes.c_int),
                 ('out_f32', ctypes.c_void_p), ('os_b', ctypes.c_longlong), ('os_c', ctypes.c_longlong),
-                ('os_y', ctypes.c_longlong), ('os_x', ctypes.c_longlong)]
+                ('os_y', ctypes.c_longlong), ('os_x', ctypes.c_longlong), ('om_octets', ctypes.c_int)]
 
 
 SYMBOLS = {

@@ -212,6 +212,25 @@ class PSA:
         return (self.B, self.C, self.H, self.W)
 
 
+class OctF32:
+    """fp32 tensor in the octet-planar layout [B][ceil(C/8)][H][W][8] (padding channels are 0): what
+    conv3x3_psa(..., f32_octets=True) writes with two 16 B stores per octet and what the tensor-core DCN reads
+    its offsets / mask from.  `.nchw()` gives the ordinary [B,C,H,W] tensor."""
+    __slots__ = ('data', 'C')
+
+    def __init__(self, data, C):
+        self.data, self.C = data, C
+
+    @property
+    def shape(self):
+        B, _, H, W, _ = self.data.shape
+        return (B, self.C, H, W)
+
+    def nchw(self):
+        B, c8, H, W, _ = self.data.shape
+        return self.data.permute(0, 1, 4, 2, 3).reshape(B, c8 * 8, H, W)[:, :self.C].contiguous()
+
+
 def psa_from_f32(x, sa=0):
     _require_cuda('x', x)
     B, C, H, W = x.shape
@@ -280,8 +299,9 @@ _ACT = {None: 0, 'none': 0, 'relu': 1, 'lrelu': 2}
 
 
 def conv3x3_psa(x, weight, bias, act=None, residual=None, residual2=None, x2=None, out=None, sa_out=0,
-                pixel_shuffle=0, out_f32=False, add_f32=None, psa_out=True, channels_last=False):
+                pixel_shuffle=0, out_f32=False, add_f32=None, psa_out=True, channels_last=False, f32_octets=False):
     """y = act(conv3x3(cat[x, x2], weight) + bias), fp32-grade on tensor cores.
+    f32_octets: the fp32 result is an OctF32 (octet-planar) instead of a strided tensor.
 
     Returns the PSA tensor `y + residual + residual2` (or PixelShuffle(2)(y)), and/or — with
     out_f32=True — the fp32 tensor `y + add_f32`.  With both, returns (psa, f32)."""
@@ -318,7 +338,12 @@ def conv3x3_psa(x, weight, bias, act=None, residual=None, residual2=None, x2=Non
         a.out_hi, a.out_lo, a.sa_out = out.hi.data_ptr(), out.lo.data_ptr(), out.sa
         ret_psa = out
     ret_f32 = None
-    if out_f32:
+    if out_f32 and f32_octets:
+        if add_f32 is not None:
+            raise RuntimeError('conv3x3_psa: add_f32 is not available with f32_octets')
+        ret_f32 = OctF32(torch.empty(x.B, (cout + 7) // 8, x.H, x.W, 8, dtype=torch.float32, device=dev), cout)
+        a.out_f32, a.out_f32_octets = ret_f32.data.data_ptr(), 1
+    elif out_f32:
         mf = torch.channels_last if channels_last else torch.contiguous_format
         ret_f32 = torch.empty(x.B, cout, x.H, x.W, dtype=torch.float32, device=dev, memory_format=mf)
         a.out_f32 = ret_f32.data_ptr()
@@ -365,7 +390,8 @@ def dcn_v2_fused_tc(x, om, weight, bias, deformable_group, pre_offset=None, idx=
                     lrelu=False, psa_out=False, out_f32=True, channels_last_out=False):
     """Tensor-core version of dcn_v2_fused_forward (3x3/s1/p1/d1).  Returns fp32 and / or PSA."""
     import ctypes
-    _require_cuda('om', om)
+    om_oct = isinstance(om, OctF32)
+    _require_cuda('om', om.data if om_oct else om)
     if isinstance(x, PSA):
         xp = x
     else:
@@ -378,12 +404,15 @@ def dcn_v2_fused_tc(x, om, weight, bias, deformable_group, pre_offset=None, idx=
     B, C, H, W = xp.shape
     dev = xp.hi.device
     cout = weight.shape[0]
-    om = om.contiguous()
     if tuple(om.shape) != (B, 27 * deformable_group, H, W):
         raise RuntimeError(f'conv_offset_mask output has shape {tuple(om.shape)}')
     a = _lib.DcnTcArgs()
     a.x_hi, a.x_lo = xp.hi.data_ptr(), xp.lo.data_ptr()
-    a.om = om.data_ptr()
+    if om_oct:
+        a.om, a.om_octets = om.data.data_ptr(), 1
+    else:
+        om = om.contiguous()
+        a.om = om.data_ptr()
     if pre_offset is not None:
         _require_cuda('pre_offset', pre_offset)
         if tuple(pre_offset.shape) != (B, 9, H, W, 2):

@@ -547,6 +547,9 @@ extern "C" int c2m_conv3x3(const c2m_conv3x3_args *a, c2m_stream_t stream) {
     p.Hout = p.ps == 2 ? 2 * a->H : a->H;
     p.Wout = p.ps == 2 ? 2 * a->W : a->W;
     p.os_b = a->os_b; p.os_c = a->os_c; p.os_y = a->os_y; p.os_x = a->os_x;
+    C2M_CHECK_ARG(!a->out_f32_octets || (a->out_f32 && !a->add_f32 && (reinterpret_cast<uintptr_t>(a->out_f32) & 15) == 0),
+                  "conv3x3: octet-planar fp32 output needs a 16 B aligned out_f32 and no add_f32");
+    p.f32_mode = !a->out_f32 ? 0 : a->out_f32_octets ? 2 : f32_store_mode(a->out_f32, a->add_f32, a->os_b, a->os_c, a->os_y, a->os_x);
     ConvPtrs q;
     q.wblob = reinterpret_cast<const uint8_t *>(a->packed_w);
     q.bias = a->bias;

@@ -48,7 +48,8 @@ constexpr int W_HDR = 256;
 struct DcnTc {
     const __half *x_hi, *x_lo; // input in the packed-split layout [B][C/8][H][W][8] (value = hi + lo)
     int C8;
-    const float *om;           // [B, 3*dg*9, H, W]
+    const float *om;           // [B, 3*dg*9, H, W], or octet-planar [B][om_c8][H][W][8] when om_c8 > 0
+    int om_c8;
     const float *pre;          // [B, 9, H, W, 2] or null
     const long long *idx;      // [B, gh, gw] or null
     int gh, gw, ref_gw, pre_scale;
@@ -285,9 +286,18 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
                 if (!live) return;
                 const int g = pair_out / 9, tap = pair_out - g * 9;
                 const int jj = g * 9 + tap, pp = y * p.W + xx;
-                mt.off_h = omb[(2 * jj) * P + pp];
-                mt.off_w = omb[(2 * jj + 1) * P + pp];
-                mt.mr = omb[(om_mask_base + jj) * P + pp];
+                if (d.om_c8 > 0) {     // 2jj is even: the (y, x) offset pair shares an octet
+                    const float *ob = d.om + (size_t)b * d.om_c8 * P * 8;
+                    const int c0 = 2 * jj, cm = om_mask_base + jj;
+                    const float2 of = *reinterpret_cast<const float2 *>(ob + ((c0 >> 3) * P + pp) * 8 + (c0 & 7));
+                    mt.off_h = of.x;
+                    mt.off_w = of.y;
+                    mt.mr = ob[((cm >> 3) * P + pp) * 8 + (cm & 7)];
+                } else {
+                    mt.off_h = omb[(2 * jj) * P + pp];
+                    mt.off_w = omb[(2 * jj + 1) * P + pp];
+                    mt.mr = omb[(om_mask_base + jj) * P + pp];
+                }
                 if (d.pre) {
                     const float2 pq = *reinterpret_cast<const float2 *>(d.pre + (((size_t)b * 9 + tap) * P + pp) * 2);
                     mt.off_w += pq.x;
@@ -537,6 +547,7 @@ extern "C" int c2m_dcn_v2_fused_tc(const c2m_dcn_tc_args *a, c2m_stream_t stream
     p.dbg = 0;
     p.C8out = (a->Cout + 7) / 8; p.Hout = a->H; p.Wout = a->W;
     p.os_b = a->os_b; p.os_c = a->os_c; p.os_y = a->os_y; p.os_x = a->os_x;
+    p.f32_mode = a->out_f32 ? f32_store_mode(a->out_f32, nullptr, a->os_b, a->os_c, a->os_y, a->os_x) : 0;
     ConvPtrs q = {};
     q.wblob = reinterpret_cast<const uint8_t *>(a->packed_w);
     q.bias = a->bias;
@@ -545,13 +556,15 @@ extern "C" int c2m_dcn_v2_fused_tc(const c2m_dcn_tc_args *a, c2m_stream_t stream
     DcnTc d;
     d.x_hi = reinterpret_cast<const __half *>(a->x_hi); d.x_lo = reinterpret_cast<const __half *>(a->x_lo);
     d.C8 = a->C / 8;
+    d.om_c8 = a->om_octets ? (27 * a->dg + 7) / 8 : 0;
+    C2M_CHECK_ARG(!a->om_octets || (reinterpret_cast<uintptr_t>(a->om) & 7) == 0, "dcn_v2_fused_tc: om must be 8 B aligned");
     d.om = a->om; d.pre = a->pre; d.idx = reinterpret_cast<const long long *>(a->idx);
     d.gh = a->gh; d.gw = a->gw; d.ref_gw = a->ref_gw; d.pre_scale = a->pre_scale;
     d.C = a->C; d.dg = a->dg; d.cpg = a->C / a->dg; d.opp = d.cpg / 8; d.n_ko = (a->C / 8) * 9;
     d.opp_shift = d.opp == 1 ? 0 : d.opp == 2 ? 1 : d.opp == 4 ? 2 : d.opp == 8 ? 3 : -1;
     d.inv_ref_gw = a->ref_gw > 0 ? 1.f / (float)a->ref_gw : 0.f;
     d.inv_scale = a->pre_scale > 0 ? 1.f / (float)a->pre_scale : 1.f;
-    C2M_CHECK_ARG((long long)a->H * a->W * 27 * a->dg < (1ll << 31) && (long long)a->H * a->W * a->C < (1ll << 31),
+    C2M_CHECK_ARG((long long)a->H * a->W * (27 * a->dg + 7) < (1ll << 31) && (long long)a->H * a->W * a->C < (1ll << 31),
                   "dcn_v2_fused_tc: map too large for 32-bit in-kernel indexing");
     C2M_CHECK_ARG(a->idx == nullptr || (long long)a->gh * a->gw < (1 << 23), "dcn_v2_fused_tc: index map too large");
     const size_t smem = (size_t)NBST * 2 * KOCT * p.N * 16 + NSTAGE * A_STAGE + 4096;

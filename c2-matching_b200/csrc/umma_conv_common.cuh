@@ -21,7 +21,15 @@ struct ConvParams {
     int dbg;                  // tuning experiments only (C2M_CONV_DBG): 1 = no global stores, 2 = no TMA reloads
     int C8out, Hout, Wout;    // geometry of the PSA output tensor
     long long os_b, os_c, os_y, os_x;   // fp32 output element strides
+    int f32_mode;             // fp32 output: 0 strided scalar stores, 1 strided with os_c == 1 (16 B stores),
+                              // 2 octet-planar [B][ceil(Cout/8)][H][W][8] (two 16 B stores per octet)
 };
+
+// fp32 output mode of a strided [B,C,H,W] view: 16 B stores need contiguous channels and aligned strides
+inline int f32_store_mode(const float *out, const float *add, long long os_b, long long os_c, long long os_y, long long os_x) {
+    const bool al = ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(add)) & 15) == 0;
+    return (os_c == 1 && al && os_b % 4 == 0 && os_y % 4 == 0 && os_x % 4 == 0) ? 1 : 0;
+}
 struct ConvPtrs {
     const uint8_t *wblob;
     const float *bias;
@@ -109,13 +117,35 @@ __device__ __forceinline__ void epilogue_store_block(const ConvPtrs &q, const Co
                             else if (p.act == 2) a = a > 0.f ? a : a * 0.1f;
                             v[j] = (j < ncol && o_base + c0 + j < p.Cout) ? a : 0.f;
                         }
-                        if (q.out_f32) {
+                        if (q.out_f32 && p.f32_mode == 2) {
     #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                const int o = o_base + c0 + j;
-                                if (j < ncol && o < p.Cout) {
-                                    const long long oi = b * p.os_b + o * p.os_c + y * p.os_y + x * p.os_x;
-                                    q.out_f32[oi] = q.add_f32 ? v[j] + q.add_f32[oi] : v[j];
+                            for (int o8 = 0; o8 < 4; ++o8) {
+                                const int oct = (o_base + c0) / 8 + o8;
+                                if (o8 * 8 >= ncol || oct >= p.C8out) break;
+                                float4 *dst = reinterpret_cast<float4 *>(
+                                    q.out_f32 + ((((size_t)b * p.C8out + oct) * p.H + y) * p.W + x) * 8);
+                                dst[0] = make_float4(v[o8 * 8], v[o8 * 8 + 1], v[o8 * 8 + 2], v[o8 * 8 + 3]);
+                                dst[1] = make_float4(v[o8 * 8 + 4], v[o8 * 8 + 5], v[o8 * 8 + 6], v[o8 * 8 + 7]);
+                            }
+                        } else if (q.out_f32) {
+                            const long long base = b * p.os_b + y * p.os_y + x * p.os_x + (long long)(o_base + c0) * p.os_c;
+    #pragma unroll
+                            for (int j4 = 0; j4 < 8; ++j4) {
+                                const int j = j4 * 4, o = o_base + c0 + j;
+                                if (p.f32_mode == 1 && j + 3 < ncol && o + 3 < p.Cout) {
+                                    float4 val = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                                    if (q.add_f32) {
+                                        const float4 ad = *reinterpret_cast<const float4 *>(q.add_f32 + base + j);
+                                        val.x += ad.x; val.y += ad.y; val.z += ad.z; val.w += ad.w;
+                                    }
+                                    *reinterpret_cast<float4 *>(q.out_f32 + base + j) = val;
+                                } else {
+    #pragma unroll
+                                    for (int k = 0; k < 4; ++k)
+                                        if (j + k < ncol && o + k < p.Cout) {
+                                            const long long oi = base + (j + k) * p.os_c;
+                                            q.out_f32[oi] = q.add_f32 ? v[j + k] + q.add_f32[oi] : v[j + k];
+                                        }
                                 }
                             }
                         }

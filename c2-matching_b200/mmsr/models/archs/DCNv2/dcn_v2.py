@@ -140,11 +140,20 @@ class DCN_sep_pre_multi_offset(_WithOffsetConv):
         returned in the packed-split layout (tensor-core kernel only)."""
         if self.stride != (1, 1) or self.dilation != (1, 1):
             raise NotImplementedError('fused pre-offset DCN supports stride 1 / dilation 1 (all C2-Matching uses)')
+        tc = (self.kernel_size == (3, 3) and self.padding == (1, 1) and lrelu_slope in (1.0, 0.1) and
+              os.environ.get('C2M_DCN_TC', '1') != '0' and
+              _ops.dcn_tc_supported(self.in_channels, self.out_channels, self.deformable_groups))
+        grad = torch.is_grad_enabled() and (getattr(om, 'requires_grad', False) or getattr(x, 'requires_grad', False) or
+                                            self.weight.requires_grad)
+        if isinstance(om, _ops.OctF32) and (self.debug_offset_check or grad or not tc):
+            om = om.nchw()       # octet-planar offsets are only understood by the tensor-core kernel
+        if isinstance(x, _ops.PSA) and (grad or not tc):
+            x = _ops.psa_to_f32(x)
         if self.debug_offset_check:
             mean = om[:, :om.shape[1] // 3 * 2].abs().mean()
             if mean > 100:
                 logger.warning(f'Offset mean is {mean}, larger than 100.')
-        if torch.is_grad_enabled() and (om.requires_grad or x.requires_grad or self.weight.requires_grad):
+        if grad:
             # training: the reference's differentiable formulation (dcn_v2.py:231-253) over dcn_v2_conv
             pre = pre_offset.materialize() if hasattr(pre_offset, 'materialize') else pre_offset
             n = om.shape[1] // 3
@@ -156,9 +165,6 @@ class DCN_sep_pre_multi_offset(_WithOffsetConv):
         idx = getattr(pre_offset, 'max_idx', None)
         kw = dict(idx=idx, pre_scale=pre_offset.scale, ref_gw=pre_offset.ref_gw) if idx is not None else \
             dict(pre_offset=pre_offset)          # ScaleOffsets handle: no offset pyramid in HBM
-        tc = (self.kernel_size == (3, 3) and self.padding == (1, 1) and lrelu_slope in (1.0, 0.1) and
-              os.environ.get('C2M_DCN_TC', '1') != '0' and
-              _ops.dcn_tc_supported(self.in_channels, self.out_channels, self.deformable_groups))
         if tc:
             return _ops.dcn_v2_fused_tc(x, om, self.weight, self.bias, self.deformable_groups, lrelu=lrelu_slope == 0.1,
                                         psa_out=want_psa, out_f32=not want_psa, channels_last_out=channels_last_out, **kw)

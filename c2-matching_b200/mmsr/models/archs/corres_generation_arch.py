@@ -95,5 +95,5 @@ class CorrespondenceGenerationArch(nn.Module):
     def forward(self, dense_features, img_ref_hr):
         idx = self.match(dense_features)
         pre_offset = PreOffsets(idx, idx.shape[2])     # decode width = INPUT grid width (:32-34)
-        img_ref_feat = self.vgg(img_ref_hr)
+        img_ref_feat = self.vgg(img_ref_hr, packed=True)     # dict of fp32 features, materialised lazily
         return pre_offset, img_ref_feat

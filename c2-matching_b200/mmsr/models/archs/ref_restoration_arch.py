@@ -77,12 +77,15 @@ class DynamicAggregationRestoration(nn.Module):
         from c2m_b200 import ops
         out = None
         for size, key, _ in _LEVELS:
-            ref = img_ref_feat[key]
-            refp = arch_util.psa_of(ref)
+            if hasattr(img_ref_feat, 'psa'):
+                ref = refp = img_ref_feat.psa(key)       # PackedFeatures: no fp32 copy of the Ref features
+            else:
+                ref = img_ref_feat[key]
+                refp = arch_util.psa_of(ref)
             dyn = getattr(self, f'{size}_dyn_agg')
             off = arch_util.conv_psa(getattr(self, f'{size}_offset_conv1'), xp, act='lrelu', x2=refp)
             off = arch_util.conv_psa(getattr(self, f'{size}_offset_conv2'), off, act='lrelu')
-            om = arch_util.conv_psa(dyn.conv_offset_mask, off, psa_out=False, out_f32=True)
+            om = arch_util.conv_psa(dyn.conv_offset_mask, off, psa_out=False, out_f32=True, f32_octets=True)
             swapped = dyn.fused_tail(ref, om, self._pre(pre_offset, key), lrelu_slope=0.1, want_psa=True)
             h = arch_util.conv_psa(getattr(self, f'head_{size}')[0], xp, act='lrelu', x2=swapped)
             h = arch_util.resblocks_psa(getattr(self, f'body_{size}'), h, final_residual2=xp)

@@ -64,8 +64,54 @@ def load_imagenet(trunk, vgg_type, path=None):
         m.bias.data.copy_(tv[f'features.{n}.bias'])
 
 
-def run_trunk(trunk, x, taps=(), want_last_f32=True):
-    """Run a named VGG trunk (Sequential of conv / relu / pool).  Returns (last, {tap: fp32}).
+class PackedFeatures(dict):
+    """{layer_name: fp32 feature} as the reference's extractor returns (vgg_arch.py:136-145), but the
+    features live in the packed-split operand layout the tcgen05 kernels consume (`.psa(name)`); the
+    fp32 tensor of a layer is produced on first access only (none is, on the fused inference path)."""
+
+    def __init__(self, packed):
+        super().__init__()
+        self._packed = dict(packed)
+
+    def psa(self, key):
+        return self._packed[key]
+
+    def __missing__(self, key):
+        from . import arch_util
+        from c2m_b200 import ops
+        if key not in self._packed:
+            raise KeyError(key)
+        t = arch_util.attach_psa(ops.psa_to_f32(self._packed[key]), self._packed[key])
+        self[key] = t
+        return t
+
+    def _fill(self):
+        for k in self._packed:
+            self[k]  # noqa: B018 — triggers __missing__
+        return self
+
+    def keys(self):
+        return dict.keys(self._fill())
+
+    def items(self):
+        return dict.items(self._fill())
+
+    def values(self):
+        return dict.values(self._fill())
+
+    def __iter__(self):
+        return dict.__iter__(self._fill())
+
+    def __contains__(self, key):
+        return key in self._packed
+
+    def __len__(self):
+        return len(self._packed)
+
+
+def run_trunk(trunk, x, taps=(), want_last_f32=True, packed_taps=False):
+    """Run a named VGG trunk (Sequential of conv / relu / pool).  Returns (last, {tap: fp32}), or
+    (last, PackedFeatures) with packed_taps when the tcgen05 path runs.
 
     tcgen05 path: each conv+ReLU pair is one launch in the packed-split layout; a tapped ReLU
     output is written both as fp32 (for the DCN sampler / the caller) and packed (attached to the
@@ -95,7 +141,8 @@ def run_trunk(trunk, x, taps=(), want_last_f32=True):
             nxt = layers[i + 2][1] if has_relu and i + 2 < len(layers) else (layers[i + 1][1] if not has_relu and i + 1 < len(layers) else None)
             last = nxt is None
             pool_next = isinstance(nxt, nn.MaxPool2d) and nxt.kernel_size in (2, (2, 2)) and nxt.stride in (2, (2, 2))
-            need_f32 = out_name in taps or (isinstance(nxt, nn.MaxPool2d) and not pool_next) or (last and want_last_f32)
+            need_f32 = (out_name in taps and not packed_taps) or (isinstance(nxt, nn.MaxPool2d) and not pool_next) or \
+                (last and want_last_f32)
             need_psa = isinstance(nxt, nn.Conv2d) or out_name in taps or pool_next
             if xp is None:
                 xp = ops.psa_from_f32(xf)
@@ -110,7 +157,7 @@ def run_trunk(trunk, x, taps=(), want_last_f32=True):
             else:
                 xp, xf = None, r
             if out_name in taps:
-                got[out_name] = xf
+                got[out_name] = xp if packed_taps else xf
             i += 2 if has_relu else 1
         elif isinstance(layer, nn.MaxPool2d):
             if xp is not None and layer.kernel_size in (2, (2, 2)) and layer.stride in (2, (2, 2)):
@@ -121,7 +168,9 @@ def run_trunk(trunk, x, taps=(), want_last_f32=True):
             i += 1
         else:
             raise RuntimeError(f'unexpected layer {name} in VGG trunk')
-    return (xf if xf is not None else ops.psa_to_f32(xp)), got
+    if xf is None and (want_last_f32 or not packed_taps):
+        xf = ops.psa_to_f32(xp)
+    return xf, (PackedFeatures(got) if packed_taps else got)
 
 
 class VGGFeatureExtractor(nn.Module):
@@ -146,8 +195,10 @@ class VGGFeatureExtractor(nn.Module):
             self.register_buffer('mean', torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1))
             self.register_buffer('std', torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1))
 
-    def forward(self, x):
+    def forward(self, x, packed=False):
+        """packed=True (inference): features stay in the tcgen05 operand layout, fp32 on demand."""
         if self.use_input_norm:
             x = (x - self.mean) / self.std
-        _, got = run_trunk(self.vgg_net, x, taps=self.layer_name_list, want_last_f32=False)
+        _, got = run_trunk(self.vgg_net, x, taps=self.layer_name_list, want_last_f32=False,
+                           packed_taps=packed and not torch.is_grad_enabled())
         return got

@@ -119,7 +119,9 @@ int c2m_dcn_v2_fused_forward_f32(const float *x, const float *om, const float *p
  * c2m_conv3x3_packed_weight_bytes(Cin,Cout) bytes (Cin = total input channels).
  *     y = act(conv(cat[in, in2], W) + bias)          act: 0 none, 1 ReLU, 2 LeakyReLU(0.1)
  *     PSA output  (optional): y + res + res2, or PixelShuffle(2)(y) when pixel_shuffle == 2
- *     fp32 output (optional): y + add_f32, strided [B,Cout,H,W]
+ *     fp32 output (optional): y + add_f32, strided [B,Cout,H,W]; or, with out_f32_octets != 0, y in the
+ *     octet-planar fp32 layout [B][ceil(Cout/8)][H][W][8] (strides and add_f32 unused; padding channels 0)
+ *     that c2m_dcn_v2_fused_tc reads its `om` operand from (om_octets)
  * Any Cin / Cout; in2 (optional) is concatenated after in along channels (then Cin % 32 == 0).
  * Needs H >= 18 and W >= 10.
  */
@@ -131,6 +133,7 @@ typedef struct {
     const void *res_hi, *res_lo, *res2_hi, *res2_lo; int sa_res;
     void *out_hi, *out_lo; int sa_out; int pixel_shuffle;
     float *out_f32; const float *add_f32; long long os_b, os_c, os_y, os_x;
+    int out_f32_octets;
 } c2m_conv3x3_args;
 
 size_t c2m_conv3x3_packed_weight_bytes(int Cin, int Cout);
@@ -160,6 +163,7 @@ typedef struct {
     const void *packed_w; const float *bias; int lrelu;
     void *out_hi, *out_lo; int sa_out;
     float *out_f32; long long os_b, os_c, os_y, os_x;
+    int om_octets;               /* != 0: om is octet-planar fp32 [B][ceil(27*dg/8)][H][W][8] */
 } c2m_dcn_tc_args;
 
 int c2m_dcn_tc_supported(int C, int Cout, int dg);

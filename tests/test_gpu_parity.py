@@ -373,7 +373,7 @@ def test_conv3x3_general_modes_vs_fp64():
     for (B, c1, c2, cout, H, W, act, mode) in ((1, 64, 256, 256, 40, 40, 'lrelu', 'psa'), (2, 64, 128, 128, 24, 40, 'lrelu', 'psa'),
                                                (1, 128, 0, 216, 36, 30, None, 'f32'), (1, 64, 0, 256, 32, 24, 'lrelu', 'ps2'),
                                                (1, 256, 0, 256, 20, 26, 'relu', 'both'), (1, 32, 0, 3, 40, 48, None, 'f32add'),
-                                               (1, 64, 64, 64, 130, 70, 'lrelu', 'psa')):
+                                               (1, 64, 64, 64, 130, 70, 'lrelu', 'psa'), (1, 64, 0, 20, 24, 24, 'relu', 'f32')):
         x1 = seeding.randn(11, (B, c1, H, W), 1.2)
         x2 = seeding.randn(12, (B, c2, H, W), 0.8) if c2 else None
         w = seeding.randn(13, (cout, c1 + c2, 3, 3), 0.03)
@@ -387,6 +387,11 @@ def test_conv3x3_general_modes_vs_fp64():
             got = ops.psa_to_f32(ops.conv3x3_psa(p1, wd, bd, act=act, x2=p2))
         elif mode == 'f32':
             got = ops.conv3x3_psa(p1, wd, bd, act=act, psa_out=False, out_f32=True)
+            oc = ops.conv3x3_psa(p1, wd, bd, act=act, psa_out=False, out_f32=True, f32_octets=True)
+            assert oc.shape == tuple(got.shape) and torch.equal(oc.nchw(), got)
+            assert float(oc.data[:, -1, :, :, cout % 8 or 8:].abs().sum()) == 0      # padding channels are zero
+            cl = ops.conv3x3_psa(p1, wd, bd, act=act, psa_out=False, out_f32=True, channels_last=True)
+            assert cl.is_contiguous(memory_format=torch.channels_last) and torch.equal(cl, got)
         elif mode == 'f32add':
             add = seeding.randn(15, (B, cout, H, W))
             got = ops.conv3x3_psa(p1, wd, bd, act=act, psa_out=False, out_f32=True, add_f32=add.to(DEV))
@@ -449,6 +454,16 @@ def test_dcn_tensor_core_vs_literal_oracle(cfg):
     gf2 = ops.dcn_v2_fused_tc(x, om, wgt, bias, dg, pre_offset=pre, lrelu=False)
     ff = c2m.dcn_v2_fused_forward(x, om, wgt, bias, dg, pre_offset=pre)
     _rel_ok(gf2, ff, 2e-5)
+    # offsets / mask handed over in the octet-planar fp32 layout: bit-identical result
+    c8 = (27 * dg + 7) // 8
+    padded = torch.zeros(B, c8 * 8, H, W, device=DEV)
+    padded[:, :27 * dg] = om
+    oct_om = ops.OctF32(padded.view(B, c8, 8, H, W).permute(0, 1, 3, 4, 2).contiguous(), 27 * dg)
+    assert torch.equal(oct_om.nchw(), om)
+    gf3 = ops.dcn_v2_fused_tc(x, oct_om, wgt, bias, dg, pre_offset=pre, lrelu=False)
+    assert torch.equal(gf3, gf2)
+    gf4 = ops.dcn_v2_fused_tc(x, om, wgt, bias, dg, pre_offset=pre, lrelu=False, channels_last_out=True)
+    assert gf4.is_contiguous(memory_format=torch.channels_last) and torch.equal(gf4, gf2)
 
 
 @pytest.mark.parametrize('cfg', [(2, 8, 6, 9, 7, 2, 3, 1, 1, 1), (1, 12, 10, 8, 10, 4, 3, 2, 2, 2), (1, 16, 16, 12, 11, 8, 3, 1, 1, 1)])
