@@ -106,6 +106,11 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
         nt = min(p.T, tiles_img - t0);
     };
 
+    // Register budget per warpgroup; the CTA's pool is what it was launched with (168 x 384 = 64512):
+    // control warpgroup 88 (the MMA issuer keeps its precomputed descriptors in registers), the two
+    // epilogue warpgroups 208 each (88 + 2 x 208 = 3 x 168): no spills on either side.
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
     if (warp == 0) {
         // ================================ activation producer ===============================
         if (lane == 0) {
@@ -216,7 +221,9 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                 if (w_resident) { bst = 0; }          // chunk kc always lives in slot kc
             }
         }
-    } else if (warp >= 4) {
+    }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
         // ================================ epilogue ==========================================
         // 8 warps: warp w owns TMEM lane quarter (w & 3) = 32 output pixels, and the 32-column block
         // c0 = 32 * ((w - 4) >> 2) of every accumulator.  (With 4 warps the serial per-thread chain
