@@ -91,6 +91,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// (A hinted variant — try_wait with a suspend-time hint, which compiles to NANOSLEEP.SYNCS — was measured
+// for the long epilogue / producer waits: no change in step time or power, so the plain probe loop stays.)
 
 // ---- TMA (cp.async.bulk.tensor), 4-D tiled load into this CTA's shared memory
 __device__ __forceinline__ void tma_prefetch_desc(const void *tmap) {

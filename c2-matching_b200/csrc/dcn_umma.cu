@@ -365,7 +365,7 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
                             if (tv && rv) { o[u][1] = r0 + 8; wq[u][1] = hh * lw; }
                             if (bv && lvv) { o[u][2] = r0 + p.W * 8; wq[u][2] = lh * hw; }
                             if (bv && rv) { o[u][3] = r0 + p.W * 8 + 8; wq[u][3] = lh * lw; }
-                            mk[u] = 1.f / (1.f + expf(-mt[u].mr));
+                            mk[u] = __fdividef(1.f, 1.f + __expf(-mt[u].mr));   // sigmoid to ~2 ulp: the TC path is fp32-grade, not bit-exact
                         }
                     }
                 }
@@ -381,31 +381,45 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
                     }
 #pragma unroll
                 for (int u = 0; u < NU; ++u) fetch(nkc_, nt_, step + 1 < n_steps, u, nx[u], npr[u], nlv[u]);
-                // ---- blend, modulate, split
+                // ---- blend, modulate, split.  value = hi + lo: the hi halves are blended in fp32, the lo halves
+                // (|lo| <= 2^-11 |value|) in packed fp16 — their rounding lands at 2^-22 of the value; the
+                // sigmoid mask is folded into the four corner weights
                 uint4 h_out[NU], l_out[NU];
 #pragma unroll
                 for (int u = 0; u < NU; ++u) {
-                    __align__(16) __half h8[8];
-                    __align__(16) __half l8[8];
-                    const __half *hp[4], *lp[4];
+                    float wm[4];
+                    __half2 wh[4];
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                        hp[c] = reinterpret_cast<const __half *>(&ch[u][c]);
-                        lp[c] = reinterpret_cast<const __half *>(&cl[u][c]);
+                        wm[c] = wq[u][c] * mk[u];
+                        wh[c] = __float2half2_rn(wm[c]);
                     }
+                    const __half2 *hp[4], *lp[4];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float a = __half2float(hp[0][j]) + __half2float(lp[0][j]);
-                        const float bq = __half2float(hp[1][j]) + __half2float(lp[1][j]);
-                        const float cq = __half2float(hp[2][j]) + __half2float(lp[2][j]);
-                        const float dq = __half2float(hp[3][j]) + __half2float(lp[3][j]);
-                        const float v = (wq[u][0] * a + wq[u][1] * bq + wq[u][2] * cq + wq[u][3] * dq) * mk[u];
-                        const __half hq = __float2half_rn(v);
-                        h8[j] = hq;
-                        l8[j] = __float2half_rn(v - __half2float(hq));
+                    for (int c = 0; c < 4; ++c) {
+                        hp[c] = reinterpret_cast<const __half2 *>(&ch[u][c]);
+                        lp[c] = reinterpret_cast<const __half2 *>(&cl[u][c]);
                     }
-                    h_out[u] = *reinterpret_cast<const uint4 *>(h8);
-                    l_out[u] = *reinterpret_cast<const uint4 *>(l8);
+                    __align__(16) __half2 h4[4];
+                    __align__(16) __half2 l4[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        __half2 ls = __hmul2(wh[0], lp[0][j]);
+                        ls = __hfma2(wh[1], lp[1][j], ls);
+                        ls = __hfma2(wh[2], lp[2][j], ls);
+                        ls = __hfma2(wh[3], lp[3][j], ls);
+                        const float2 lf = __half22float2(ls);
+                        const float2 a = __half22float2(hp[0][j]), bq = __half22float2(hp[1][j]);
+                        const float2 cq = __half22float2(hp[2][j]), dq = __half22float2(hp[3][j]);
+                        const float vx = fmaf(wm[0], a.x, fmaf(wm[1], bq.x, fmaf(wm[2], cq.x, fmaf(wm[3], dq.x, lf.x))));
+                        const float vy = fmaf(wm[0], a.y, fmaf(wm[1], bq.y, fmaf(wm[2], cq.y, fmaf(wm[3], dq.y, lf.y))));
+                        const __half2 hq = __floats2half2_rn(vx, vy);
+                        const float2 hf = __half22float2(hq);
+                        h4[j] = hq;
+                        l4[j] = __floats2half2_rn(vx - hf.x, vy - hf.y);
+                    }
+                    h_out[u] = *reinterpret_cast<const uint4 *>(h4);
+                    l_out[u] = *reinterpret_cast<const uint4 *>(l4);
                 }
                 TR(if (trc) g_tr[trs][1] = gtime();)
                 mbar_wait(&empty[stage], phase ^ 1);
