@@ -43,7 +43,7 @@ enum {
     C2M_ERR_UNSUPPORTED = 4   /* no sm_100 device / driver entry point missing */
 };
 
-int c2m_abi_version(void);
+int c2m_abi_version(void);      /* 2 since c2m_conv3x3_args.out_f32_octets / c2m_dcn_tc_args.om_octets */
 const char *c2m_last_error(void);
 
 /* --- correlation / index_map --------------------------------------------------------------
