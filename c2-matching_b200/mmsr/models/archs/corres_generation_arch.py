@@ -65,6 +65,9 @@ class PreOffsets(dict):
     def __contains__(self, key):
         return key in _SCALES
 
+    def get(self, key, default=None):
+        return self[key] if key in _SCALES else default
+
     def __len__(self):
         return len(_SCALES)
 

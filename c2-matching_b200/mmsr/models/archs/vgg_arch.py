@@ -105,6 +105,9 @@ class PackedFeatures(dict):
     def __contains__(self, key):
         return key in self._packed
 
+    def get(self, key, default=None):
+        return self[key] if key in self._packed else default
+
     def __len__(self):
         return len(self._packed)
 

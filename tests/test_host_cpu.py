@@ -205,3 +205,48 @@ def test_dataset_matches_reference_dataset_golden(tmp_path):
             assert np.array_equal(s[k].numpy(), g[f'{i}/{k}']), (i, k)
         assert bool(s['padding']) == bool(g[f'{i}/padding'])
         assert list(s['original_size']) == list(g[f'{i}/original_size'])
+
+
+def test_lazy_result_dicts_behave_like_the_reference_dicts(monkeypatch):
+    """`pre_offset` / `img_ref_feat` of CorrespondenceGenerationArch.forward are plain dicts in the
+    reference (corres_generation_arch.py:107-116); here they fill themselves on first access.
+    Host logic only: the device conversions are replaced by CPU stand-ins."""
+    import torch
+    from c2m_b200 import ops
+    from mmsr.models.archs import corres_generation_arch as cg
+    from mmsr.models.archs import vgg_arch
+
+    calls = []
+
+    def fake_to_f32(p, add=None, channels_last=False):
+        calls.append(p)
+        return torch.full((1, 2, 3, 3), float(p))
+
+    monkeypatch.setattr(ops, 'psa_to_f32', fake_to_f32)
+    feats = vgg_arch.PackedFeatures({'relu1_1': 1, 'relu2_1': 2})
+    assert len(feats) == 2 and 'relu1_1' in feats and 'relu3_1' not in feats and not calls
+    assert feats.psa('relu2_1') == 2 and not calls
+    assert float(feats['relu2_1'].mean()) == 2.0 and calls == [2]
+    assert feats['relu2_1'] is feats['relu2_1'] and calls == [2]           # cached
+    assert feats.get('relu3_1') is None and feats.get('relu1_1').shape == (1, 2, 3, 3)
+    assert sorted(feats.keys()) == ['relu1_1', 'relu2_1'] and len(list(feats.items())) == 2
+    try:
+        feats['relu9_9']
+        raise AssertionError('missing layer must raise KeyError')
+    except KeyError:
+        pass
+
+    built = []
+
+    def fake_pyramid(idx, scale, ref_gw=None):
+        built.append(scale)
+        return torch.zeros(1, 9, 4 * scale, 4 * scale, 2)
+
+    monkeypatch.setattr(cg._ops, 'offset_pyramid', fake_pyramid)
+    pre = cg.PreOffsets(torch.zeros(1, 2, 2, dtype=torch.int64), 2)
+    assert len(pre) == 3 and 'relu2_1' in pre and not built
+    h = pre.handle('relu1_1')
+    assert (h.scale, h.ref_gw) == (4, 2) and not built
+    assert pre['relu2_1'].shape == (1, 9, 8, 8, 2) and built == [2]
+    assert pre.get('nope', 7) == 7 and set(pre.keys()) == {'relu1_1', 'relu2_1', 'relu3_1'}
+    assert sorted(built) == [1, 2, 4]
