@@ -1,4 +1,5 @@
-"""Diagnostic run on the GPU box: every kernel vs the oracle, mismatch statistics printed (no
+"""Test infrastructure (kept under tests/ because it calls the oracle): diagnostic run on the GPU box,
+every kernel vs the oracle, mismatch statistics printed (no
 asserts) so one gpurun call tells as much as possible.  Not a test, not a benchmark."""
 import os
 import sys
