@@ -11,12 +11,12 @@ GPU (BASELINE config 2), random-init weights of the real architecture.  Weak sca
 processes its own batch, no data-path collective; `value` = images of all ranks / max-over-ranks
 time.
 
-One JSON line on rank 0 (see the task contract): value (inputs resident in HBM), e2e (host
-pinned inputs -> H2D -> forward -> D2H of the SR images, through the public
-RestorationPipeline.run_host call), roofline of the dominant kernel (the tcgen05 correlation
-search, timed live with CUDA events on its own stream by the library's profiling hook),
-cpu_baseline (the oracle port of the reference's CPU path on this box's host cores, bounded
-sample), clocks, gpu_launches.
+One JSON line on rank 0 (see the task contract): value (inputs resident in HBM; timed with the library's
+profiling hook OFF), e2e (host pinned inputs -> H2D -> forward -> D2H of the SR images, through the public
+RestorationPipeline.run_host call), roofline of the dominant kernel class (per-launch CUDA events recorded by
+the library on the launching stream in a SEPARATE pass), cpu_baseline (the oracle port of the reference's CPU
+path on this box's physical host cores, bounded sample), parity (image 0 of the timed batch: GPU pipeline vs
+that same oracle run), micro (BASELINE configs 3 and 4), clocks, gpu_launches.
 """
 import argparse
 import json
@@ -30,6 +30,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (ROOT, os.path.join(ROOT, 'c2-matching_b200'), os.path.join(ROOT, 'tests', 'golden')):
     if p not in sys.path:
         sys.path.insert(0, p)
+
+# random-init (seeded) weights of the real architecture: no ImageNet VGG checkpoint exists on the box
+os.environ.setdefault('C2M_VGG_PRETRAINED', '0')
 
 import torch  # noqa: E402
 
@@ -93,22 +96,47 @@ def corr_algorithmic(batch):
     return flops, byts
 
 
-def cpu_baseline(sample_images=1, threads=None):
-    """The reference's CPU path (oracle port, kind "port": the reference is Python and
-    /root/reference does not exist on the GPU box) on a bounded sample of the same workload."""
-    import seeding  # noqa: F401
-    from c2m_b200.pipeline import synthetic_pair
+def host_cores():
+    """(physical, logical) core counts of this host; the CPU legs run on the physical ones."""
+    logical = os.cpu_count() or 1
+    try:
+        import psutil
+        physical = psutil.cpu_count(logical=False) or logical
+    except Exception:
+        physical = logical
+    return physical, logical
+
+
+def cpu_baseline(pair, timed_runs=3, b4_budget_s=120.0):
+    """The reference's CPU path (oracle port, kind "port": the reference is Python and /root/reference does not
+    exist on the GPU box) on a bounded sample of the SAME workload: image 0 of rank 0's timed batch, 1 warm-up +
+    `timed_runs` runs at batch 1 (the reference's own validation batch size), and one batch-4 run when it fits
+    the time budget.  Returns (record, (sr, idx) of the oracle on that image) — the latter feeds `parity`."""
     from oracle import ref_path
-    threads = threads or os.cpu_count() or 1
-    torch.set_num_threads(threads)
-    sd_e, sd_m, sd_g = seeded_weights()
-    img_lq, img_up, img_ref = synthetic_pair(1234, sample_images, LR, REF)
+    physical, logical = host_cores()
+    torch.set_num_threads(physical)
+    sds = seeded_weights()
+    one = [t[:1] for t in pair]
     t0 = time.perf_counter()
-    ref_path.full_forward(sd_e, sd_m, sd_g, img_lq, img_up, img_ref)
-    dt = time.perf_counter() - t0
-    return {'value': sample_images / dt, 'unit': 'images/s', 'cores': threads, 'kind': 'port',
-            'sample': f'{sample_images} image(s) of the workload, full forward, fp32 torch-CPU oracle port '
-                      f'(oracle/ref_path.py), {dt:.1f} s'}
+    want = ref_path.full_forward(*sds, *one, return_idx=True)          # warm-up run; its result is the parity oracle
+    warm = time.perf_counter() - t0
+    runs = []
+    for _ in range(timed_runs):
+        t0 = time.perf_counter()
+        ref_path.full_forward(*sds, *one)
+        runs.append(time.perf_counter() - t0)
+    mean = sum(runs) / len(runs)
+    rec = {'value': 1.0 / mean, 'unit': 'images/s', 'cores': physical, 'logical_cores': logical, 'kind': 'port',
+           'runs_s': [round(r, 2) for r in runs], 'warmup_s': round(warm, 2),
+           'sample': f'image 0 of the timed batch, full forward at batch 1, {timed_runs} timed runs after 1 warm-up, fp32 '
+                     f'torch-CPU oracle port (oracle/ref_path.py), {physical} threads = physical cores'}
+    if pair[0].shape[0] >= 4 and 4 * mean <= b4_budget_s:
+        four = [t[:4] for t in pair]
+        t0 = time.perf_counter()
+        ref_path.full_forward(*sds, *four)
+        dt = time.perf_counter() - t0
+        rec['batch4'] = {'value': 4.0 / dt, 'unit': 'images/s', 'runs_s': [round(dt, 2)]}
+    return rec, want
 
 
 # ------------------------------------------------------------------------------- reference arm
@@ -117,10 +145,10 @@ def run_reference(args, rank):
         return
     from c2m_b200.pipeline import synthetic_pair
     from oracle import ref_path
-    threads = os.cpu_count() or 1
+    threads, logical = host_cores()
     torch.set_num_threads(threads)
     sd_e, sd_m, sd_g = seeded_weights()
-    img_lq, img_up, img_ref = synthetic_pair(1234, 1, LR, REF)     # bounded sample: 1 image per step
+    img_lq, img_up, img_ref = [t[:1] for t in synthetic_pair(1234, BATCH, LR, REF)]     # bounded sample: image 0, 1 image per step
     budget_s = 200.0
     t_est = None
     for _ in range(max(1, min(args.warmup, 1))):
@@ -134,7 +162,7 @@ def run_reference(args, rank):
     dt = time.perf_counter() - t0
     v = steps / dt
     sample = (f'1 image per step (config-2 shapes), {steps} timed steps of {args.steps} requested, '
-              f'torch-CPU oracle port of the reference path, {threads} threads')
+              f'torch-CPU oracle port of the reference path, {threads} threads = physical cores ({logical} logical)')
     print(json.dumps({
         'impl': 'reference', 'metric': 'SR images/sec (160x160->640x640, 500x500 Ref)', 'value': v, 'unit': 'images/s',
         'n_gpus': args.gpus, 'steps': steps, 'warmup': 1, 'ms_per_step': dt / steps * 1e3, 'higher_is_better': True,
@@ -206,16 +234,21 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    ops.profile_enable(True)
-    for k in ops.PROF_KERNELS:
-        ops.profile_collect(k)
+    # (1) the headline numbers: library profiling hook OFF, nothing but the step inside the events
+    ops.profile_enable(False)
     n0 = c2m.launch_count()
     ms_dev = timed(step_dev, args.steps)
     launches = c2m.launch_count() - n0
-    prof = {k: ops.profile_collect(k) for k in ops.PROF_KERNELS}
-    ops.profile_enable(False)
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop() if sampler else None
+    # (2) separate pass for the per-kernel-class device times (2 cudaEventRecord per launch: not part of `value`)
+    prof_steps = max(1, min(args.steps, 5))
+    ops.profile_enable(True)
+    for k in ops.PROF_KERNELS:
+        ops.profile_collect(k)
+    ms_prof = timed(step_dev, prof_steps)
+    prof = {k: ops.profile_collect(k) for k in ops.PROF_KERNELS}
+    ops.profile_enable(False)
 
     imgs = BATCH * args.steps * world
     value = imgs / (ms_dev / 1e3)
@@ -236,8 +269,8 @@ def run_ours(args, rank, world, local_rank):
         classes = {}
         for k, r in prof.items():
             if r['launches']:
-                classes[k] = {'ms_per_step': r['ms'] / args.steps, 'launches_per_step': r['launches'] / args.steps,
-                              'share_of_step': r['ms'] / ms_dev if world == 1 else None,
+                classes[k] = {'ms_per_step': r['ms'] / prof_steps, 'launches_per_step': r['launches'] / prof_steps,
+                              'share_of_step': r['ms'] / ms_prof,
                               'algorithmic_tflops': r['flops'] / (r['ms'] / 1e3) / 1e12,
                               'algorithmic_gbps': r['bytes'] / (r['ms'] / 1e3) / 1e9}
         dom = max(prof, key=lambda k: prof[k]['ms'])
@@ -265,21 +298,38 @@ def run_ours(args, rank, world, local_rank):
                             'partial products (hi*hi + hi*lo + lo*hi = x3 issued MMA work), so the '
                             'tensor-pipe busy fraction is `issued_over_algorithmic_mma` x `frac`',
                     'per_kernel_class': classes}
-        cpu = None
+        cpu = parity = micro = None
         if world == 1 and not args.no_cpu_baseline:
-            cpu = cpu_baseline(1)
+            # same seeded pair for the CPU leg and the GPU: image 0 of the timed batch.  The oracle's result is
+            # kept and the GPU pipeline is checked against it (checker use of oracle/, never on the timed path).
+            from parity_util import full_forward_parity
+            cpu, want = cpu_baseline((img_lq, img_up, img_ref))
+            parity = full_forward_parity(pipe, seeded_weights(), img_lq[:1], img_up[:1], img_ref[:1], want=want)
+            parity['note'] = ('image 0 of the timed batch vs oracle/ref_path.full_forward on the same inputs: idx_flips = '
+                              'queries whose index differs from the oracle end to end (features from tcgen05 convs vs '
+                              'oneDNN), max_gap64_of_flips = largest fp64 score difference between the two candidates of '
+                              'a flipped query, sr_max_rel_err = SR vs the oracle restoration evaluated on this run\'s own '
+                              'index map, psnr_delta_db = |PSNR(ours) - PSNR(oracle end to end)| with the reference metric')
+        if world == 1 and not args.no_micro:
+            sys.path.insert(0, os.path.join(ROOT, 'tools'))
+            import microbench
+            micro = {'peak_tflops': peaks.get('bf16_tflops') or 1590.0, 'peak_hbm_gbs': peaks.get('hbm_gbs') or 6650.0,
+                     'peaks': 'MEASURED_PEAKS.json burst figures (kernels timed alone)' if peaks else 'fallback',
+                     'rows': microbench.run_config3(dev, flush, peaks.get('bf16_tflops') or 1590.0) +
+                             microbench.run_config4(dev, flush, peaks.get('hbm_gbs') or 6650.0)}
         print(json.dumps({
             'metric': 'SR images/sec (160x160->640x640, 500x500 Ref)', 'value': value, 'unit': 'images/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
             'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'global_batch': BATCH * world, 'parallelism': f'dp{world} (batch-sharded pairs, no data-path collective)',
-                       'l2': 'flushed between timed steps (192 MiB fill)', 'weights': 'random-init (seeded), real architecture',
+                       'l2': 'flushed between timed steps (192 MiB fill)', 'profiling_hook': 'off while `value` / `e2e` are timed', 'weights': 'random-init (seeded), real architecture',
                        'convs': 'hand-written tcgen05 3x3 kernel, split-fp16 operands, fp32 accumulate (fp32-grade); '
                                 'cuDNN is not on the path', 'cudnn_tf32_allowed': bool(args.tf32)},
             'e2e': {'value': e2e, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': ms_e2e / args.steps, 'api': 'c2m_b200.pipeline.RestorationPipeline.run_host'},
-            'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu, 'clocks': clocks,
+            'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu, 'parity': parity, 'micro': micro,
+            'clocks': clocks,
         }), flush=True)
     if dist_on:
         torch.distributed.destroy_process_group()
@@ -293,7 +343,8 @@ def main():
     ap.add_argument('--impl', choices=['ours', 'reference'], default='ours')
     ap.add_argument('--tf32', type=int, default=0, help='allow cuDNN TF32 for the plain convolutions (default: exact fp32)')
     ap.add_argument('--channels-last', type=int, default=0)
-    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the CPU oracle leg (cpu_baseline + parity)')
+    ap.add_argument('--no-micro', action='store_true', help='skip the config-3 / config-4 microbenchmarks')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))

@@ -44,7 +44,8 @@ class DcnTcArgs(ctypes.Structure):
                 ('packed_w', ctypes.c_void_p), ('bias', ctypes.c_void_p), ('lrelu', ctypes.c_int),
                 ('out_hi', ctypes.c_void_p), ('out_lo', ctypes.c_void_p), ('sa_out', ctypes.c_int),
                 ('out_f32', ctypes.c_void_p), ('os_b', ctypes.c_longlong), ('os_c', ctypes.c_longlong),
-                ('os_y', ctypes.c_longlong), ('os_x', ctypes.c_longlong), ('om_octets', ctypes.c_int)]
+                ('os_y', ctypes.c_longlong), ('os_x', ctypes.c_longlong), ('om_octets', ctypes.c_int),
+                ('mask', ctypes.c_void_p)]
 
 
 SYMBOLS = {
@@ -85,6 +86,9 @@ class C2MError(RuntimeError):
     pass
 
 
+EXPECTED_ABI = 3      # c2m_abi_version() the ctypes structs above mirror (include/c2m_sm100.h)
+
+
 def lib():
     global _lib
     if _lib is None:
@@ -97,6 +101,10 @@ def lib():
             fn = getattr(l, name)          # AttributeError if the .so does not export it
             fn.restype = res
             fn.argtypes = args
+        got = l.c2m_abi_version()
+        if got != EXPECTED_ABI:
+            raise C2MError(f'{LIB_PATH} has ABI version {got}, these bindings are written for {EXPECTED_ABI}: '
+                           'rebuild it (python -c "import __graft_entry__ as g; g.build()")')
         _lib = l
     return _lib
 

@@ -143,6 +143,13 @@ def dcn_v2_forward(input, weight, bias, offset, mask, kernel_h, kernel_w, stride
     T = kernel_h * kernel_w
     if tuple(offset.shape) != (B, 2 * deformable_group * T, Ho, Wo) or tuple(mask.shape) != (B, deformable_group * T, Ho, Wo):
         raise RuntimeError(f'offset/mask shape mismatch: {tuple(offset.shape)}, {tuple(mask.shape)} for output {Ho}x{Wo}')
+    import os
+    if ((kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h, dilation_w) == (3, 3, 1, 1, 1, 1, 1, 1) and
+            dcn_tc_supported(C, weight.shape[0], deformable_group) and os.environ.get('C2M_EXT_DCN_TC', '1') != '0'):
+        # eligible shapes (every DCN of C2-Matching) take the tensor-core kernel: fp32 NCHW -> packed-split operand
+        # in one pass, final offsets / mask read as given, fp32 NCHW out.  The FFMA kernel below stays the general
+        # path (any kernel size / stride / dilation / group width).
+        return dcn_v2_fused_tc(x, offset.contiguous(), weight, bias, deformable_group, final_mask=mask.contiguous())
     out = torch.empty(B, weight.shape[0], Ho, Wo, dtype=torch.float32, device=x.device)
     s = _shape(x, weight.shape[0], kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h, dilation_w,
                deformable_group, out)
@@ -272,27 +279,64 @@ def conv3x3_supported(cin, cout, H=None, W=None):
     return H is None or (H >= 18 and W >= 10)
 
 
-def conv3x3_pack_weights(weight):
-    """Pack a [Cout,Cin,3,3] fp32 weight for c2m_conv3x3_psa.  The blob is cached ON the tensor
-    object (so it dies with it — a global cache keyed by data_ptr would alias a freed parameter's
-    address) and re-made when the storage or the version counter changes."""
-    _require_cuda('weight', weight)
-    tag = (weight.data_ptr(), weight._version, tuple(weight.shape))
-    cached = getattr(weight, '_c2m_pack', None)
+# ---- packed-weight cache.  The blob lives ON the tensor object (so it dies with it — a global cache keyed
+# by data_ptr would alias a freed parameter's address) and is re-made when the storage, the shape or the
+# version counter changes.  Writes through `.data` do NOT bump the version: call invalidate_packs() after
+# such an edit (load_state_dict / `with torch.no_grad(): p.copy_()` do bump it).
+_fallback_packs = {}          # id(tensor) -> (weakref, {attr: entry}) for tensors that refuse attributes
+
+
+def _pack_cached(weight, attr, extra, make):
+    import weakref
+    tag = (weight.data_ptr(), weight._version, tuple(weight.shape), extra)
+    store = getattr(weight, '__dict__', None)
+    if store is None:
+        ent = _fallback_packs.get(id(weight))
+        if ent is None or ent[0]() is not weight:
+            key = id(weight)
+            ent = (weakref.ref(weight, lambda _r, key=key: _fallback_packs.pop(key, None)), {})
+            _fallback_packs[key] = ent
+        store = ent[1]
+    cached = store.get(attr)
+    cur = torch.cuda.current_stream(weight.device)
     if cached is not None and cached[0] == tag:
-        return cached[1]
-    cout, cin = weight.shape[:2]
-    n = _lib.lib().c2m_conv3x3_packed_weight_bytes(cin, cout)
-    blob = torch.empty(n, dtype=torch.uint8, device=weight.device)
-    with torch.cuda.device(weight.device):
-        rc = _lib.lib().c2m_conv3x3_pack_weights_f32(weight.detach().contiguous().data_ptr(), cin, cout,
-                                                     blob.data_ptr(), _stream())
-        _lib.check(rc, 'c2m_conv3x3_pack_weights_f32')
-    try:
-        weight._c2m_pack = (tag, blob)
-    except Exception:
-        pass
+        _, blob, ev, st = cached
+        if st != cur.cuda_stream:
+            cur.wait_event(ev)            # packed on another stream: order this stream after the pack kernels
+        return blob
+    blob = make()
+    ev = torch.cuda.Event()
+    ev.record(cur)
+    store[attr] = (tag, blob, ev, cur.cuda_stream)
     return blob
+
+
+def invalidate_packs(obj):
+    """Drop the cached packed weights of a tensor, or of every parameter of a module (needed after in-place
+    edits through `.data`, which do not bump the tensor version)."""
+    tensors = [obj] if isinstance(obj, torch.Tensor) else list(obj.parameters())
+    for t in tensors:
+        d = getattr(t, '__dict__', None)
+        if d is not None:
+            d.pop('_c2m_pack', None)
+            d.pop('_c2m_dcn_pack', None)
+        _fallback_packs.pop(id(t), None)
+
+
+def conv3x3_pack_weights(weight):
+    """Pack a [Cout,Cin,3,3] fp32 weight for c2m_conv3x3_psa (cached, see _pack_cached)."""
+    _require_cuda('weight', weight)
+    cout, cin = weight.shape[:2]
+
+    def make():
+        n = _lib.lib().c2m_conv3x3_packed_weight_bytes(cin, cout)
+        blob = torch.empty(n, dtype=torch.uint8, device=weight.device)
+        with torch.cuda.device(weight.device):
+            rc = _lib.lib().c2m_conv3x3_pack_weights_f32(weight.detach().contiguous().data_ptr(), cin, cout,
+                                                         blob.data_ptr(), _stream())
+            _lib.check(rc, 'c2m_conv3x3_pack_weights_f32')
+        return blob
+    return _pack_cached(weight, '_c2m_pack', None, make)
 
 
 _ACT = {None: 0, 'none': 0, 'relu': 1, 'lrelu': 2}
@@ -368,27 +412,24 @@ def dcn_tc_supported(C, Cout, dg, kh=3, kw=3):
 
 
 def _dcn_tc_pack(weight, dg):
-    tag = (weight.data_ptr(), weight._version, tuple(weight.shape), dg)
-    cached = getattr(weight, '_c2m_dcn_pack', None)
-    if cached is not None and cached[0] == tag:
-        return cached[1]
     cout, c = weight.shape[:2]
-    n = _lib.lib().c2m_dcn_tc_packed_weight_bytes(c, cout, dg)
-    blob = torch.empty(n, dtype=torch.uint8, device=weight.device)
-    with torch.cuda.device(weight.device):
-        rc = _lib.lib().c2m_dcn_tc_pack_weights_f32(weight.detach().contiguous().data_ptr(), c, cout, dg,
-                                                    blob.data_ptr(), _stream())
-        _lib.check(rc, 'c2m_dcn_tc_pack_weights_f32')
-    try:
-        weight._c2m_dcn_pack = (tag, blob)
-    except Exception:
-        pass
-    return blob
+
+    def make():
+        n = _lib.lib().c2m_dcn_tc_packed_weight_bytes(c, cout, dg)
+        blob = torch.empty(n, dtype=torch.uint8, device=weight.device)
+        with torch.cuda.device(weight.device):
+            rc = _lib.lib().c2m_dcn_tc_pack_weights_f32(weight.detach().contiguous().data_ptr(), c, cout, dg,
+                                                        blob.data_ptr(), _stream())
+            _lib.check(rc, 'c2m_dcn_tc_pack_weights_f32')
+        return blob
+    return _pack_cached(weight, '_c2m_dcn_pack', dg, make)
 
 
 def dcn_v2_fused_tc(x, om, weight, bias, deformable_group, pre_offset=None, idx=None, pre_scale=1, ref_gw=None,
-                    lrelu=False, psa_out=False, out_f32=True, channels_last_out=False):
-    """Tensor-core version of dcn_v2_fused_forward (3x3/s1/p1/d1).  Returns fp32 and / or PSA."""
+                    lrelu=False, psa_out=False, out_f32=True, channels_last_out=False, final_mask=None):
+    """Tensor-core version of dcn_v2_fused_forward (3x3/s1/p1/d1).  Returns fp32 and / or PSA.
+    final_mask: `om` then holds the FINAL offsets [B,2*dg*9,H,W] and final_mask the FINAL modulation
+    [B,dg*9,H,W] (the `_ext.dcn_v2_forward` contract: no pre-offsets, no sigmoid)."""
     import ctypes
     om_oct = isinstance(om, OctF32)
     _require_cuda('om', om.data if om_oct else om)
@@ -404,9 +445,18 @@ def dcn_v2_fused_tc(x, om, weight, bias, deformable_group, pre_offset=None, idx=
     B, C, H, W = xp.shape
     dev = xp.hi.device
     cout = weight.shape[0]
-    if tuple(om.shape) != (B, 27 * deformable_group, H, W):
+    if final_mask is not None:
+        _require_cuda('final_mask', final_mask)
+        if om_oct or pre_offset is not None or idx is not None:
+            raise RuntimeError('dcn_v2_fused_tc: final_mask excludes octet-planar om and pre-offsets')
+        if tuple(om.shape) != (B, 18 * deformable_group, H, W) or tuple(final_mask.shape) != (B, 9 * deformable_group, H, W):
+            raise RuntimeError(f'offset/mask shape mismatch: {tuple(om.shape)}, {tuple(final_mask.shape)}')
+    elif tuple(om.shape) != (B, 27 * deformable_group, H, W):
         raise RuntimeError(f'conv_offset_mask output has shape {tuple(om.shape)}')
     a = _lib.DcnTcArgs()
+    if final_mask is not None:
+        final_mask = final_mask.contiguous()
+        a.mask = final_mask.data_ptr()
     a.x_hi, a.x_lo = xp.hi.data_ptr(), xp.lo.data_ptr()
     if om_oct:
         a.om, a.om_octets = om.data.data_ptr(), 1

@@ -87,9 +87,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Bounded wait: a protocol bug (lost arrive, register-pool deadlock, ...) must end in a trap that the
+// host sees as a launch failure, not in a kernel that spins until the GPU lease is killed.  One try_wait
+// probe suspends for up to ~1 us, so the limit below is tens of seconds; -DC2M_MBAR_SPIN_LIMIT=0 removes
+// the counter.
+#ifndef C2M_MBAR_SPIN_LIMIT
+#define C2M_MBAR_SPIN_LIMIT (1u << 26)
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+#if C2M_MBAR_SPIN_LIMIT
+    uint32_t n = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++n > C2M_MBAR_SPIN_LIMIT) __trap();   // no printf here: it would put a stack frame into every role loop
+    }
+#else
     while (!mbar_try_wait(bar, parity)) {
     }
+#endif
 }
 // (A hinted variant — try_wait with a suspend-time hint, which compiles to NANOSLEEP.SYNCS — was measured
 // for the long epilogue / producer waits: no change in step time or power, so the plain probe loop stays.)

@@ -291,11 +291,8 @@ int corr_search_umma_launch(const CorrGeom &g, const CorrWorkspace &ws, cudaStre
     p.rt_per_chunk = ceil_div(p.rt_x * p.rt_y, ws.nchunk);
     p.NQ = g.NQ; p.NR = g.NR;
 
-    static bool attr_set = false;
-    if (!attr_set) {
-        C2M_CUDA(cudaFuncSetAttribute(corr_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        attr_set = true;
-    }
+    // per launch: the attribute belongs to the (device, context) pair, not to the process
+    C2M_CUDA(cudaFuncSetAttribute(corr_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     int dev = 0, sms = 0;
     C2M_CUDA(cudaGetDevice(&dev));
     C2M_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

@@ -50,6 +50,8 @@ struct DcnTc {
     int C8;
     const float *om;           // [B, 3*dg*9, H, W], or octet-planar [B][om_c8][H][W][8] when om_c8 > 0
     int om_c8;
+    const float *mask;         // non-null: FINAL modulation mask [B, dg*9, H, W] (no sigmoid) and `om` holds only the
+                               // FINAL offsets [B, 2*dg*9, H, W] — the `_ext.dcn_v2_forward` contract
     const float *pre;          // [B, 9, H, W, 2] or null
     const long long *idx;      // [B, gh, gw] or null
     int gh, gw, ref_gw, pre_scale;
@@ -257,7 +259,7 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
         struct Meta { float off_h, off_w, mr; int v; };
         int stage = 0, phase = 0;
         const float inv_ti = 1.f / (float)tiles_img;
-        const size_t x_img = (size_t)d.C8 * P * 8, om_img = (size_t)3 * d.dg * 9 * P;
+        const size_t x_img = (size_t)d.C8 * P * 8, om_img = (size_t)(d.mask ? 2 : 3) * d.dg * 9 * P;
         for (int pos = w_begin, nt = 0; pos < w_end; pos += nt) {
             int slice;
             group(pos, slice, nt);
@@ -296,7 +298,7 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
                 } else {
                     mt.off_h = omb[(2 * jj) * P + pp];
                     mt.off_w = omb[(2 * jj + 1) * P + pp];
-                    mt.mr = omb[(om_mask_base + jj) * P + pp];
+                    mt.mr = d.mask ? d.mask[((size_t)b * d.dg * 9 + jj) * P + pp] : omb[(om_mask_base + jj) * P + pp];
                 }
                 if (d.pre) {
                     const float2 pq = *reinterpret_cast<const float2 *>(d.pre + (((size_t)b * 9 + tap) * P + pp) * 2);
@@ -365,7 +367,8 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
                             if (tv && rv) { o[u][1] = r0 + 8; wq[u][1] = hh * lw; }
                             if (bv && lvv) { o[u][2] = r0 + p.W * 8; wq[u][2] = lh * hw; }
                             if (bv && rv) { o[u][3] = r0 + p.W * 8 + 8; wq[u][3] = lh * lw; }
-                            mk[u] = __fdividef(1.f, 1.f + __expf(-mt[u].mr));   // sigmoid to ~2 ulp: the TC path is fp32-grade, not bit-exact
+                            // sigmoid to ~2 ulp: the TC path is fp32-grade, not bit-exact
+                            mk[u] = d.mask ? mt[u].mr : __fdividef(1.f, 1.f + __expf(-mt[u].mr));
                         }
                     }
                 }
@@ -572,6 +575,9 @@ extern "C" int c2m_dcn_v2_fused_tc(const c2m_dcn_tc_args *a, c2m_stream_t stream
     d.C8 = a->C / 8;
     d.om_c8 = a->om_octets ? (27 * a->dg + 7) / 8 : 0;
     C2M_CHECK_ARG(!a->om_octets || (reinterpret_cast<uintptr_t>(a->om) & 7) == 0, "dcn_v2_fused_tc: om must be 8 B aligned");
+    C2M_CHECK_ARG(!a->mask || (!a->om_octets && !a->pre && !a->idx),
+                  "dcn_v2_fused_tc: a final mask excludes octet-planar om and pre-offsets");
+    d.mask = a->mask;
     d.om = a->om; d.pre = a->pre; d.idx = reinterpret_cast<const long long *>(a->idx);
     d.gh = a->gh; d.gw = a->gw; d.ref_gw = a->ref_gw; d.pre_scale = a->pre_scale;
     d.C = a->C; d.dg = a->dg; d.cpg = a->C / a->dg; d.opp = d.cpg / 8; d.n_ko = (a->C / 8) * 9;

@@ -75,12 +75,15 @@ class PreOffsets(dict):
 class CorrespondenceGenerationArch(nn.Module):
 
     def __init__(self, patch_size=3, stride=1, vgg_layer_list=('relu3_1', 'relu2_1', 'relu1_1'),
-                 vgg_type='vgg19', vgg_pretrained_path=None):
+                 vgg_type='vgg19', vgg_pretrained=None, vgg_pretrained_path=None):
+        """Reference signature (corres_generation_arch.py:16-27) + two optional kwargs: the reference builds
+        `vgg19(pretrained=True)` here and never loads net_map from a checkpoint, so by default the ImageNet
+        weights are REQUIRED (local checkpoint or torch hub cache; raises otherwise)."""
         super().__init__()
         self.patch_size, self.stride = patch_size, stride
         self.vgg_layer_list = list(vgg_layer_list)
         self.vgg = VGGFeatureExtractor(layer_name_list=self.vgg_layer_list, vgg_type=vgg_type,
-                                       pretrained_path=vgg_pretrained_path)
+                                       pretrained=vgg_pretrained, pretrained_path=vgg_pretrained_path)
 
     def index_to_flow(self, max_idx):
         """[h,w] index map -> [1,h+2,w+2,2] (x,y) flow, zero-padded (corres…:29-46)."""

@@ -49,19 +49,58 @@ def build_trunk(vgg_type, last_layer, pooling_stride=2, remove_pooling=False):
     return nn.Sequential(seq)
 
 
+_TV_FILES = {'vgg11': 'vgg11-8a719046.pth', 'vgg13': 'vgg13-19584684.pth', 'vgg16': 'vgg16-397923af.pth',
+             'vgg19': 'vgg19-dcbb9e9d.pth'}
+
+
+def find_imagenet_checkpoint(vgg_type, path=None):
+    """Where the torchvision ImageNet checkpoint of `vgg_type` is on this machine, or None:
+    explicit path -> $C2M_<VGG_TYPE>_WEIGHTS -> the torch hub cache torchvision downloads into."""
+    import os
+    cands = [path, os.environ.get(f'C2M_{vgg_type.upper()}_WEIGHTS')]
+    try:
+        cands.append(os.path.join(torch.hub.get_dir(), 'checkpoints', _TV_FILES[vgg_type]))
+    except Exception:
+        pass
+    for c in cands:
+        if c and os.path.isfile(c):
+            return c
+    return None
+
+
 def load_imagenet(trunk, vgg_type, path=None):
-    """Copy torchvision ImageNet weights (`features.N.*`) into a named trunk.  `path`: a local
-    torchvision vgg checkpoint; if None, torchvision's cache is tried (no network here)."""
-    if path is not None:
-        tv = torch.load(path, map_location='cpu')
+    """Copy torchvision ImageNet weights (`features.N.*`) into a named trunk — what the reference's
+    constructor does with `vgg19(pretrained=True)` (vgg_arch.py:103-104).  Resolution: `path`,
+    $C2M_VGG19_WEIGHTS, the torch hub cache, then torchvision's own download.  Raises when none of them
+    yields weights: a net_map with random VGG weights gives silently wrong SR images."""
+    found = find_imagenet_checkpoint(vgg_type, path)
+    if path is not None and found != path:
+        raise FileNotFoundError(f'VGG checkpoint {path} not found')
+    if found is not None:
+        tv = torch.load(found, map_location='cpu')
     else:
-        import torchvision
-        tv = getattr(torchvision.models, vgg_type)(weights='IMAGENET1K_V1').state_dict()
+        try:
+            import torchvision
+            tv = getattr(torchvision.models, vgg_type)(weights='IMAGENET1K_V1').state_dict()
+        except Exception as e:
+            raise RuntimeError(
+                f'ImageNet weights for {vgg_type} are not available (no local checkpoint, download failed: {e}). '
+                f'Put torchvision\'s {_TV_FILES.get(vgg_type)} into the torch hub cache, point '
+                f'$C2M_{vgg_type.upper()}_WEIGHTS / the `vgg_pretrained_path` option at it, or pass vgg_pretrained=False '
+                f'(C2M_VGG_PRETRAINED=0) if random VGG weights are intended (synthetic benchmarks).') from e
     convs = [m for m in trunk if isinstance(m, nn.Conv2d)]
     keys = sorted({int(k.split('.')[1]) for k in tv if k.startswith('features.')})
-    for m, n in zip(convs, keys):
-        m.weight.data.copy_(tv[f'features.{n}.weight'])
-        m.bias.data.copy_(tv[f'features.{n}.bias'])
+    with torch.no_grad():      # in-place copy_ on the parameter bumps its version -> packed-weight caches refresh
+        for m, n in zip(convs, keys):
+            m.weight.copy_(tv[f'features.{n}.weight'])
+            m.bias.copy_(tv[f'features.{n}.bias'])
+
+
+def pretrained_default():
+    """The reference always builds its VGGs with pretrained=True; C2M_VGG_PRETRAINED=0 (set by the
+    synthetic tests / bench, which have no ImageNet checkpoint) turns that off process-wide."""
+    import os
+    return os.environ.get('C2M_VGG_PRETRAINED', '1') != '0'
 
 
 class PackedFeatures(dict):
@@ -180,7 +219,7 @@ class VGGFeatureExtractor(nn.Module):
     """Returns {layer_name: feature} for the requested layers — vgg_arch.py:59-145."""
 
     def __init__(self, layer_name_list, vgg_type='vgg19', use_input_norm=True, requires_grad=False,
-                 remove_pooling=False, pooling_stride=2, pretrained_path=None):
+                 remove_pooling=False, pooling_stride=2, pretrained=None, pretrained_path=None):
         super().__init__()
         if 'bn' in vgg_type:
             raise NotImplementedError('batch-norm VGG variants are not used by C2-Matching')
@@ -189,7 +228,11 @@ class VGGFeatureExtractor(nn.Module):
         self.names = layer_names(vgg_type)
         last = max(self.layer_name_list, key=self.names.index)
         self.vgg_net = build_trunk(vgg_type, last, pooling_stride, remove_pooling)
-        if pretrained_path is not None:
+        # reference: `vgg19(pretrained=True)` in the constructor (vgg_arch.py:103-104); `pretrained=False`
+        # / C2M_VGG_PRETRAINED=0 are this build's explicit opt-outs for synthetic weights
+        if pretrained is None:
+            pretrained = pretrained_default() or pretrained_path is not None
+        if pretrained:
             load_imagenet(self.vgg_net, vgg_type, pretrained_path)
         if not requires_grad:
             for p in self.parameters():

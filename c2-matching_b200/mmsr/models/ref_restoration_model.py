@@ -31,11 +31,22 @@ class RefRestorationModel:
         if not torch.cuda.is_available():
             raise RuntimeError('RefRestorationModel needs a CUDA device: the B200 hot path has no CPU fallback')
         self.device = torch.device('cuda', torch.cuda.current_device())
+        path = opt.get('path') or {}
+        # parity is stated against the reference's fp32 arithmetic: any convolution that falls back to cuDNN
+        # (maps below the tcgen05 tile size, C2M_FAST_CONV=0) must not run in TF32 (torch's default)
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        # net_map's VGG19 is never loaded from a checkpoint in the reference: it is built with ImageNet weights
+        # (vgg_arch.py:103-104).  Optional `path.pretrain_model_vgg` names a local torchvision checkpoint.
+        if path.get('pretrain_model_vgg') and opt.get('network_map') is not None:
+            opt['network_map'].setdefault('vgg_pretrained_path', path['pretrain_model_vgg'])
         self.net_g = networks.define_net_g(opt).to(self.device).eval()
         self.net_map = networks.define_net_map(opt).to(self.device).eval()
         self.net_extractor = networks.define_net_extractor(opt).to(self.device).eval()
-        path = opt.get('path') or {}
         strict = path.get('strict_load', True)
+        for key in ('pretrain_model_feature_extractor', 'pretrain_model_g'):
+            if not path.get(key):
+                logger.warning(f'path.{key} is not set: the network keeps its random initial weights.')
         if path.get('pretrain_model_feature_extractor'):
             self.load_network(self.net_extractor, path['pretrain_model_feature_extractor'], strict)
         if path.get('pretrain_model_g'):

@@ -43,7 +43,7 @@ enum {
     C2M_ERR_UNSUPPORTED = 4   /* no sm_100 device / driver entry point missing */
 };
 
-int c2m_abi_version(void);      /* 2 since c2m_conv3x3_args.out_f32_octets / c2m_dcn_tc_args.om_octets */
+int c2m_abi_version(void);      /* 3 since c2m_dcn_tc_args.mask (2: out_f32_octets / om_octets) */
 const char *c2m_last_error(void);
 
 /* --- correlation / index_map --------------------------------------------------------------
@@ -164,6 +164,9 @@ typedef struct {
     void *out_hi, *out_lo; int sa_out;
     float *out_f32; long long os_b, os_c, os_y, os_x;
     int om_octets;               /* != 0: om is octet-planar fp32 [B][ceil(27*dg/8)][H][W][8] */
+    const float *mask;           /* != NULL: the `_ext.dcn_v2_forward` contract (DCNv2/src/dcn_v2.h:9-22) — `om` is the
+                                  * FINAL offset tensor [B,2*dg*9,H,W], `mask` the FINAL modulation [B,dg*9,H,W]
+                                  * (no sigmoid applied); pre, idx and om_octets must be unset */
 } c2m_dcn_tc_args;
 
 int c2m_dcn_tc_supported(int C, int Cout, int dg);

@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# tests run on seeded synthetic weights: there is no ImageNet VGG checkpoint on the box (no network), so the
+# reference's `vgg19(pretrained=True)` default is switched off explicitly (tests/test_host_cpu.py covers the default)
+os.environ.setdefault('C2M_VGG_PRETRAINED', '0')
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, 'c2-matching_b200'), os.path.join(ROOT, 'tests', 'golden')):
     if p not in sys.path:

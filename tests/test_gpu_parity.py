@@ -160,10 +160,17 @@ def _dcn_case_tensors(case):
     return x, wgt, bias, off, mask
 
 
+@pytest.mark.parametrize('route', ['tensor_core_when_eligible', 'ffma'])
 @pytest.mark.parametrize('channels_last', [False, True])
 @pytest.mark.parametrize('case', mg.DCN_CASES, ids=[c[0] for c in mg.DCN_CASES])
-def test_ext_dcn_v2_forward_vs_literal_oracle(case, channels_last):
+def test_ext_dcn_v2_forward_vs_literal_oracle(case, channels_last, route, monkeypatch):
+    """B1 boundary.  3x3/s1/p1/d1 shapes with C/dg % 8 == 0 ('wide' here, every DCN of the model) are routed to
+    the tcgen05 kernel (split-fp16 contraction: 2e-5 of the output scale vs the fp64-accumulating oracle);
+    everything else, and everything with C2M_EXT_DCN_TC=0, runs the operation-for-operation FFMA kernel (1e-5)."""
     import _ext
+    from c2m_b200 import ops
+    if route == 'ffma':
+        monkeypatch.setenv('C2M_EXT_DCN_TC', '0')
     dg = case[6]
     x, wgt, bias, off, mask = _dcn_case_tensors(case)
     want = c_oracle.dcn_v2_forward(x, wgt, bias, off, mask, dg=dg, acc64=True)
@@ -172,7 +179,8 @@ def test_ext_dcn_v2_forward_vs_literal_oracle(case, channels_last):
         xd = xd.contiguous(memory_format=torch.channels_last)
     got = _ext.dcn_v2_forward(xd, wgt.to(DEV), bias.to(DEV), off.to(DEV), mask.to(DEV), 3, 3, 1, 1, 1, 1, 1, 1, dg)
     assert got.shape == want.shape and got.is_contiguous()
-    _rel_ok(got.cpu(), want, 1e-5)
+    tc = route != 'ffma' and ops.dcn_tc_supported(x.shape[1], wgt.shape[0], dg)
+    _rel_ok(got.cpu(), want, 2e-5 if tc else 1e-5)
 
 
 def test_ext_dcn_strided_dilated_and_big_cout():
@@ -406,6 +414,19 @@ def test_conv3x3_general_modes_vs_fp64():
         assert err <= 3e-5 * float(want.abs().max()), (mode, err)
 
 
+def _module_path_on_idx(pipe, args, idx_given):
+    """Run the pipeline's nets under the CURRENT environment switches (cuDNN convs / FFMA DCN), but feed the
+    restoration net the pre-offsets of `idx_given`: isolates the conv / DCN numerics from index flips.
+    Returns (sr, the index map this path would have found itself)."""
+    from mmsr.models.archs.corres_generation_arch import PreOffsets
+    lq, up, ref = args
+    with torch.no_grad():
+        feats = pipe.net_extractor(up, ref)
+        pre, ref_feat = pipe.net_map(feats, ref)
+        sr = pipe.net_g(lq, PreOffsets(idx_given, idx_given.shape[2]), ref_feat)
+    return sr, pre.max_idx
+
+
 def test_fast_conv_path_equals_cudnn_path(monkeypatch):
     """The whole pipeline with every plain conv on the tcgen05 kernel vs the same pipeline with
     them on exact-fp32 cuDNN (C2M_FAST_CONV=0): same index map, SR within 1e-3 relative."""
@@ -416,11 +437,9 @@ def test_fast_conv_path_equals_cudnn_path(monkeypatch):
     args = [t.to(DEV) for t in (img_lq, img_up, img_ref)]
     sr_fast, idx_fast = pipe.forward(*args, return_idx=True)
     monkeypatch.setenv('C2M_FAST_CONV', '0')
-    sr_slow, idx_slow = pipe.forward(*args, return_idx=True)
-    flips = int((idx_fast != idx_slow).sum())
-    assert flips <= 2
-    if flips == 0:
-        _rel_ok(sr_fast, sr_slow, 1e-3)
+    sr_slow, idx_slow = _module_path_on_idx(pipe, args, idx_fast)
+    assert int((idx_fast != idx_slow).sum()) <= 2
+    _rel_ok(sr_fast, sr_slow, 1e-3)          # always: the module path is evaluated on the fast path's index map
 
 
 @pytest.mark.parametrize('cfg', [(1, 64, 64, 8, 10, 12, 2), (2, 16, 16, 2, 20, 9, 1), (1, 128, 128, 8, 9, 9, 2),
@@ -590,9 +609,7 @@ def test_non_square_pipeline_fast_vs_module_path(monkeypatch):
     sr_fast, idx_fast = pipe.forward(*args, return_idx=True)
     monkeypatch.setenv('C2M_FAST_CONV', '0')
     monkeypatch.setenv('C2M_DCN_TC', '0')
-    sr_slow, idx_slow = pipe.forward(*args, return_idx=True)
+    sr_slow, idx_slow = _module_path_on_idx(pipe, args, idx_fast)
     assert tuple(sr_fast.shape) == (1, 3, 4 * lr_h, 4 * lr_w)
-    flips = int((idx_fast != idx_slow).sum())
-    assert flips <= 3, flips
-    if flips == 0:
-        _rel_ok(sr_fast, sr_slow, 1e-3)
+    assert int((idx_fast != idx_slow).sum()) <= 3
+    _rel_ok(sr_fast, sr_slow, 1e-3)          # always: the module path is evaluated on the fast path's index map

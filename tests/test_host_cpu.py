@@ -37,7 +37,7 @@ def test_library_exports_every_declared_symbol(built):
     assert set(declared) <= exported, set(declared) - exported
     assert set(built.SYMBOLS) == set(declared)          # the ctypes table binds all of them
     lib = built.lib()
-    assert lib.c2m_abi_version() == 2
+    assert lib.c2m_abi_version() == 3
 
 
 def test_sass_is_blackwell_native(built):
@@ -250,3 +250,42 @@ def test_lazy_result_dicts_behave_like_the_reference_dicts(monkeypatch):
     assert pre['relu2_1'].shape == (1, 9, 8, 8, 2) and built == [2]
     assert pre.get('nope', 7) == 7 and set(pre.keys()) == {'relu1_1', 'relu2_1', 'relu3_1'}
     assert sorted(built) == [1, 2, 4]
+
+
+def test_net_map_vgg_defaults_to_imagenet_weights(tmp_path, monkeypatch):
+    """the reference builds net_map's VGG19 with `pretrained=True` and never loads it from a
+    checkpoint (vgg_arch.py:103-104), so the reference YAML (no extra key) must yield ImageNet weights here too —
+    from a local torchvision checkpoint — and must RAISE when there are none, not run on random weights."""
+    import torchvision
+    from mmsr.models import networks
+    from mmsr.models.archs.corres_generation_arch import CorrespondenceGenerationArch
+    monkeypatch.setenv('C2M_VGG_PRETRAINED', '1')                      # undo the test-suite opt-out
+    monkeypatch.setattr(torch.hub, 'get_dir', lambda: str(tmp_path / 'hub'))
+    def no_network(*a, **k):
+        raise OSError('no network in the test')
+    monkeypatch.setattr(torchvision.models, 'vgg19', no_network)
+    with pytest.raises(RuntimeError, match='ImageNet weights for vgg19 are not available'):
+        CorrespondenceGenerationArch(3, 1, ['relu1_1', 'relu2_1', 'relu3_1'], 'vgg19')
+    # a torchvision-format checkpoint (features.N.*) in the hub cache is picked up by the reference YAML's kwargs
+    tv = {}
+    for n, (ci, co) in zip((0, 2, 5, 7, 10), ((3, 64), (64, 64), (64, 128), (128, 128), (128, 256))):
+        tv[f'features.{n}.weight'] = seeding.randn(n + 1, (co, ci, 3, 3))
+        tv[f'features.{n}.bias'] = seeding.randn(n + 50, (co,))
+    ck = tmp_path / 'hub' / 'checkpoints'
+    ck.mkdir(parents=True)
+    torch.save(tv, ck / 'vgg19-dcbb9e9d.pth')
+    opt = {'network_map': {'type': 'CorrespondenceGenerationArch', 'patch_size': 3, 'stride': 1,
+                           'vgg_layer_list': ['relu1_1', 'relu2_1', 'relu3_1'], 'vgg_type': 'vgg19'}}
+    net = networks.define_net_map(opt)
+    assert torch.equal(net.vgg.vgg_net.conv1_1.weight, tv['features.0.weight'])
+    assert torch.equal(net.vgg.vgg_net.conv3_1.bias, tv['features.10.bias'])
+    # explicit path / explicit opt-out
+    other = tmp_path / 'my_vgg19.pth'
+    tv2 = {k: v + 1 for k, v in tv.items()}
+    torch.save(tv2, other)
+    net2 = CorrespondenceGenerationArch(vgg_pretrained_path=str(other))
+    assert torch.equal(net2.vgg.vgg_net.conv2_1.weight, tv2['features.5.weight'])
+    net3 = CorrespondenceGenerationArch(vgg_pretrained=False)
+    assert not torch.equal(net3.vgg.vgg_net.conv1_1.weight, tv['features.0.weight'])
+    with pytest.raises(FileNotFoundError):
+        CorrespondenceGenerationArch(vgg_pretrained_path=str(tmp_path / 'missing.pth'))
