@@ -79,9 +79,12 @@ static void carve(CorrWorkspace &ws, const CorrGeom &g, uint8_t *base) {
     ws.ss_in = (float *)take(pin * 4);
     ws.ss_ref = (float *)take(pref * 4);
     ws.rinv = (float *)take((size_t)g.B * g.NR * 4);
-    ws.part = (Candidate *)take((size_t)g.B * 16 * g.NQ * sizeof(Candidate));   // nchunk <= 16
-    ws.amax_bits = (unsigned *)take(256);
+    ws.part = (Candidate *)take((size_t)g.B * CORR_MAX_CHUNKS * g.NQ * sizeof(Candidate));
+    ws.ovf = (CorrOverflow *)take((size_t)g.B * g.NQ * sizeof(CorrOverflow));
+    ws.amax_bits = (unsigned *)take(256);            // zeroed at the start of every call
     ws.sexp = (int *)(ws.amax_bits ? ws.amax_bits + 8 : nullptr);
+    ws.ovf_count = ws.amax_bits ? ws.amax_bits + 16 : nullptr;
+    ws.max_pn_bits = ws.amax_bits ? ws.amax_bits + 17 : nullptr;
     ws.total_bytes = off;
 }
 
@@ -119,22 +122,34 @@ extern "C" int c2m_corr_argmax_f32(const float *fin, const float *fref, int B, i
     C2M_CUDA(cudaMemsetAsync(ws.amax_bits, 0, 256, st));
 
     const bool use_umma = !(flags & 1u) && corr_umma_supported(g);
+    CorrChunkGeom cg;
+    float window_coef;
+    const int K = g.C * g.patch * g.patch;
     if (use_umma) {
-        int dev = 0, major = 0;
+        int dev = 0, major = 0, sms = 0;
         C2M_CUDA(cudaGetDevice(&dev));
         C2M_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+        C2M_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         if (major != 10) {
             set_error("corr_argmax: tcgen05 path needs an sm_100 device (found sm_%d*)", major);
             return C2M_ERR_UNSUPPORTED;
         }
-        ws.nchunk = corr_umma_pick_nchunk(g);
+        ws.nchunk = corr_umma_pick_nchunk(g, sms);
+        corr_umma_chunk_geom(g, ws.nchunk, cg);
+        // |approx - exact| <= 2^-22 * (K/16 + 3) * ||P_q|| * ||P_r|| * rinv_r  (K/16 tcgen05 instructions
+        // feed each score, 1 fp32 ulp of (|acc| + sum|products|) each, + the 2^-22 operand split); the window is
+        // twice that (best and candidate both err), times 2 of slack for the tensor core's internal alignment
+        window_coef = ldexpf(1.f, -20) * (float)((K + 15) / 16 + 3);
     } else {
         int n = ceil_div(4 * 148, g.B * ceil_div(g.NQ, 64));
         const int ntile = ceil_div(g.NR, 64);
-        if (n > 16) n = 16;
+        if (n > CORR_MAX_CHUNKS) n = CORR_MAX_CHUNKS;
         if (n > ntile) n = ntile;
         if (n < 1) n = 1;
         ws.nchunk = n;
+        corr_generic_chunk_geom(g, ws.nchunk, cg);
+        // sequential fp32 FMA chain of K terms: |approx - exact| <= K * 2^-24 * ||P_q|| * ||P_r|| * rinv_r (+ the final scale)
+        window_coef = ldexpf(1.f, -23) * (float)(K + 4);
     }
 
     if ((rc = corr_prep_launch(fin, B, C, g.Cp, h * w, l2norm, 0, ws, ws.p32_in, ws.hi_in, ws.lo_in, ws.ss_in, st))) return rc;
@@ -146,7 +161,7 @@ extern "C" int c2m_corr_argmax_f32(const float *fin, const float *fref, int B, i
     rc = use_umma ? corr_search_umma_launch(g, ws, st) : corr_search_generic_launch(g, ws, st);
     if (rc) return rc;
     prof_end(ph, st);
-    return corr_rescore_launch(g, ws, is_norm, norm_input, idx, val, st);
+    return corr_rescore_launch(g, ws, cg, window_coef, is_norm, norm_input, idx, val, st);
 }
 
 extern "C" int c2m_profile_enable(int on) {

@@ -139,25 +139,28 @@ int corr_prep_launch(const float *x, int B, int C, int Cp, int HW, int l2norm, i
 // rinv[b][r] = 1 / (sqrt(sum over the patch's pixels of ss) + 1e-5)      (ref_map_util.py:63)
 // ------------------------------------------------------------------------------------------
 __global__ void rinv_kernel(const float *__restrict__ ss, float *__restrict__ rinv, int hr, int wr, int rh, int rw,
-                            int patch, int s_ref, int is_norm) {
+                            int patch, int s_ref, int is_norm, unsigned *__restrict__ max_pn_bits) {
     const int b = blockIdx.y;
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= rh * rw) return;
-    float v = 1.f;
-    if (is_norm) {
+    float pn = 0.f;
+    if (r < rh * rw) {
         const int ry = (r / rw) * s_ref, rx = (r % rw) * s_ref;
         const float *s = ss + (size_t)b * hr * wr;
         float acc = 0.f;
         for (int dy = 0; dy < patch; ++dy)
             for (int dx = 0; dx < patch; ++dx) acc += s[(ry + dy) * wr + rx + dx];
-        v = 1.f / (sqrtf(acc) + 1e-5f);
+        pn = sqrtf(acc);
+        rinv[(size_t)b * rh * rw + r] = is_norm ? 1.f / (pn + 1e-5f) : 1.f;
     }
-    rinv[(size_t)b * rh * rw + r] = v;
+    // largest Ref patch norm of the call: scales the rescoring window when the scores are not normalised
+#pragma unroll
+    for (int o = 16; o; o >>= 1) pn = fmaxf(pn, __shfl_xor_sync(0xffffffffu, pn, o));
+    if ((threadIdx.x & 31) == 0 && pn > 0.f) atomicMax(max_pn_bits, __float_as_uint(pn));
 }
 
 int corr_rinv_launch(const CorrGeom &g, const CorrWorkspace &ws, int is_norm, cudaStream_t st) {
     dim3 grid(ceil_div(g.NR, 256), g.B);
-    rinv_kernel<<<grid, 256, 0, st>>>(ws.ss_ref, ws.rinv, g.hr, g.wr, g.rh, g.rw, g.patch, g.s_ref, is_norm);
+    rinv_kernel<<<grid, 256, 0, st>>>(ws.ss_ref, ws.rinv, g.hr, g.wr, g.rh, g.rw, g.patch, g.s_ref, is_norm, ws.max_pn_bits);
     C2M_LAUNCH_CHECK("rinv_kernel");
     return C2M_OK;
 }
@@ -272,6 +275,12 @@ __global__ void __launch_bounds__(256) search_generic_kernel(const float *__rest
     }
 }
 
+void corr_generic_chunk_geom(const CorrGeom &g, int nchunk, CorrChunkGeom &cg) {
+    cg.mode = 0;
+    cg.per = ceil_div(ceil_div(g.NR, GS_T), nchunk) * GS_T;       // same split as search_generic_kernel
+    cg.n_rt = cg.rt_x = cg.tile_rows = cg.tile_cols = 0;
+}
+
 int corr_search_generic_launch(const CorrGeom &g, const CorrWorkspace &ws, cudaStream_t st) {
     dim3 grid(ceil_div(g.NQ, GS_T), ws.nchunk, g.B);
     search_generic_kernel<<<grid, 256, 0, st>>>(ws.p32_in, ws.p32_ref, ws.rinv, ws.part, g, ws.nchunk);
@@ -280,11 +289,16 @@ int corr_search_generic_launch(const CorrGeom &g, const CorrWorkspace &ws, cudaS
 }
 
 // ------------------------------------------------------------------------------------------
-// Exact rescoring: one warp per query.  Among the candidates whose approximate score is within
-// a relative 5e-4 of the best approximate score, recompute
+// Exact rescoring.  The searches rank Ref patches by an APPROXIMATE score s~ (tensor-core / fp32-FMA rounding);
+// the index map is defined on the exact one,
 //     s(r) = float( sum_k double(q[k]) * double( float(ref[k] / (float(sqrt(ss_r)) + 1e-5f)) ) )
-// — the reference's arithmetic (Ref patch normalised in fp32 first, ref_map_util.py:63) with an
-// error-free accumulation — and keep the max (lowest index on ties).
+// — the reference's arithmetic (Ref patch normalised in fp32 first, ref_map_util.py:63) with an error-free
+// accumulation.  With |s~(r) - s(r)| <= E for every r (E = window/2, DESIGN.md K2 derives it from the number of
+// accumulation steps and the operand split), the exact argmax r* satisfies s~(r*) >= max s~ - 2E, so it is enough
+// to rescore every candidate inside that window.  The searches keep a top-2 per (query, Ref chunk): the list of a
+// chunk is COMPLETE unless its second entry is itself inside the window (then a third one could be hiding); those
+// (query, chunk) pairs go to an overflow list and `rescore_overflow_kernel` re-scans the whole chunk exactly.
+// Hence idx/val equal the exhaustive exact result, whatever the tensor cores rounded.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -292,10 +306,48 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// exact score of (query pixel qp, Ref pixel rp), computed by one warp; every lane returns it
+__device__ __forceinline__ float exact_score_warp(const float *__restrict__ pinb, const float *__restrict__ prefb,
+                                                  const CorrGeom &g, int qp, int rp, int is_norm, int lane) {
+    const int taps = g.patch * g.patch;
+    float denom = 1.f;
+    if (is_norm) {
+        double ss = 0.0;
+        for (int tap = 0; tap < taps; ++tap) {
+            const float *row = prefb + (size_t)(rp + (tap / g.patch) * g.wr + tap % g.patch) * g.Cp;
+            for (int c = lane; c < g.Cp; c += 32) ss += (double)row[c] * (double)row[c];
+        }
+        ss = warp_sum(ss);
+        denom = (float)sqrt(ss) + 1e-5f;
+    }
+    double acc = 0.0;
+    for (int tap = 0; tap < taps; ++tap) {
+        const int dy = tap / g.patch, dx = tap % g.patch;
+        const float *rrow = prefb + (size_t)(rp + dy * g.wr + dx) * g.Cp;
+        const float *qrow = pinb + (size_t)(qp + dy * g.w + dx) * g.Cp;
+        for (int c = lane; c < g.Cp; c += 32) {
+            const float pn = is_norm ? __fdiv_rn(rrow[c], denom) : rrow[c];
+            acc += (double)qrow[c] * (double)pn;
+        }
+    }
+    return (float)warp_sum(acc);
+}
+
+__device__ __forceinline__ double query_patch_ss(const float *__restrict__ pinb, const CorrGeom &g, int qp, int lane) {
+    double ssq = 0.0;
+    for (int tap = 0; tap < g.patch * g.patch; ++tap) {
+        const float *row = pinb + (size_t)(qp + (tap / g.patch) * g.w + tap % g.patch) * g.Cp;
+        for (int c = lane; c < g.Cp; c += 32) ssq += (double)row[c] * (double)row[c];
+    }
+    return warp_sum(ssq);
+}
+
 __global__ void __launch_bounds__(256) rescore_kernel(const float *__restrict__ pin, const float *__restrict__ pref,
                                                       const Candidate *__restrict__ part, CorrGeom g, int nchunk,
+                                                      float window_coef, const unsigned *__restrict__ max_pn_bits,
                                                       int is_norm, int norm_input, int64_t *__restrict__ idx,
-                                                      float *__restrict__ val) {
+                                                      float *__restrict__ val, CorrOverflow *__restrict__ ovf,
+                                                      unsigned *__restrict__ ovf_count) {
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int b = blockIdx.y;
@@ -303,75 +355,159 @@ __global__ void __launch_bounds__(256) rescore_kernel(const float *__restrict__ 
     const float *pinb = pin + (size_t)b * g.h * g.w * g.Cp;
     const float *prefb = pref + (size_t)b * g.hr * g.wr * g.Cp;
     const int qp = ((q / g.gw) * g.s_in) * g.w + (q % g.gw) * g.s_in;
-    const int taps = g.patch * g.patch;
 
-    // candidates: lane l < 2*nchunk holds one
-    float cv = -INFINITY;
-    int ci = -1;
-    if (lane < 2 * nchunk) {
-        const Candidate c = part[((size_t)b * nchunk + (lane >> 1)) * g.NQ + q];
-        cv = (lane & 1) ? c.v2 : c.v1;
-        ci = (lane & 1) ? c.i2 : c.i1;
-        if (ci < 0) cv = -INFINITY;
+    // candidates: slot c = 2 * chunk + {0: best, 1: second}; lane l holds slots l and l + 32 (nchunk <= 32)
+    float cv[2];
+    int ci[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int slot = lane + 32 * k;
+        cv[k] = -INFINITY;
+        ci[k] = -1;
+        if (slot < 2 * nchunk) {
+            const Candidate c = part[((size_t)b * nchunk + (slot >> 1)) * g.NQ + q];
+            cv[k] = (slot & 1) ? c.v2 : c.v1;
+            ci[k] = (slot & 1) ? c.i2 : c.i1;
+            if (ci[k] < 0) cv[k] = -INFINITY;
+        }
     }
-    float vmax = cv;
+    float vmax = fmaxf(cv[0], cv[1]);
 #pragma unroll
     for (int o = 16; o; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-    const float thr = vmax - (5e-4f * fabsf(vmax) + 1e-30f);
-    unsigned sel = __ballot_sync(0xffffffffu, ci >= 0 && cv >= thr);
 
-    // query patch norm
-    double ssq = 0.0;
-    if (norm_input) {
-        for (int tap = 0; tap < taps; ++tap) {
-            const float *row = pinb + (size_t)(qp + (tap / g.patch) * g.w + tap % g.patch) * g.Cp;
-            for (int c = lane; c < g.Cp; c += 32) ssq += (double)row[c] * (double)row[c];
+    // window = 2E: proportional to the query patch norm (and to the largest Ref patch norm when scores are raw)
+    const double ssq = query_patch_ss(pinb, g, qp, lane);
+    const float qn = (float)sqrt(ssq);
+    const float window = window_coef * qn * (is_norm ? 1.f : __uint_as_float(*max_pn_bits)) + 1e-30f;
+    const float thr = vmax - window;
+
+    // chunks whose SECOND entry is inside the window may hide further candidates -> exhaustive re-scan
+    unsigned ovf_mask = 0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int slot = lane + 32 * k;
+        const bool hit = (slot & 1) && ci[k] >= 0 && cv[k] >= thr;
+        unsigned m = __ballot_sync(0xffffffffu, hit);
+        while (m) {
+            const int l = __ffs(m) - 1;
+            m &= m - 1;
+            ovf_mask |= 1u << ((l + 32 * k) >> 1);
         }
-        ssq = warp_sum(ssq);
     }
 
     float best = -INFINITY;
     int besti = 0x7fffffff;
-    while (sel) {
-        const int src = __ffs(sel) - 1;
-        sel &= sel - 1;
-        const int r = __shfl_sync(0xffffffffu, ci, src);
-        const int rp = ((r / g.rw) * g.s_ref) * g.wr + (r % g.rw) * g.s_ref;
-        float denom = 1.f;
-        if (is_norm) {
-            double ss = 0.0;
-            for (int tap = 0; tap < taps; ++tap) {
-                const float *row = prefb + (size_t)(rp + (tap / g.patch) * g.wr + tap % g.patch) * g.Cp;
-                for (int c = lane; c < g.Cp; c += 32) ss += (double)row[c] * (double)row[c];
-            }
-            ss = warp_sum(ss);
-            denom = (float)sqrt(ss) + 1e-5f;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        unsigned sel = __ballot_sync(0xffffffffu, ci[k] >= 0 && cv[k] >= thr);
+        while (sel) {
+            const int src = __ffs(sel) - 1;
+            sel &= sel - 1;
+            const int r = __shfl_sync(0xffffffffu, ci[k], src);
+            if ((ovf_mask >> ((src + 32 * k) >> 1)) & 1u) continue;      // the re-scan covers this chunk anyway
+            const int rp = ((r / g.rw) * g.s_ref) * g.wr + (r % g.rw) * g.s_ref;
+            const float s = exact_score_warp(pinb, prefb, g, qp, rp, is_norm, lane);
+            if (cand_better(s, r, best, besti)) { best = s; besti = r; }
         }
-        double acc = 0.0;
-        for (int tap = 0; tap < taps; ++tap) {
-            const int dy = tap / g.patch, dx = tap % g.patch;
-            const float *rrow = prefb + (size_t)(rp + dy * g.wr + dx) * g.Cp;
-            const float *qrow = pinb + (size_t)(qp + dy * g.w + dx) * g.Cp;
-            for (int c = lane; c < g.Cp; c += 32) {
-                const float pn = is_norm ? __fdiv_rn(rrow[c], denom) : rrow[c];
-                acc += (double)qrow[c] * (double)pn;
-            }
-        }
-        acc = warp_sum(acc);
-        const float s = (float)acc;
-        if (cand_better(s, r, best, besti)) { best = s; besti = r; }
     }
     if (lane == 0) {
-        idx[(size_t)b * g.NQ + q] = besti == 0x7fffffff ? 0 : besti;
-        val[(size_t)b * g.NQ + q] = norm_input ? best / ((float)sqrt(ssq) + 1e-5f) : best;
+        // raw best score; rescore_overflow_kernel / finish_kernel apply the input-norm division afterwards
+        idx[(size_t)b * g.NQ + q] = besti == 0x7fffffff ? -1 : besti;
+        val[(size_t)b * g.NQ + q] = best;
+        if (ovf_mask) {
+            const unsigned n = atomicAdd(ovf_count, 1u);
+            ovf[n] = CorrOverflow{b * g.NQ + q, ovf_mask};           // capacity B * NQ: one entry per query at most
+        }
     }
 }
 
-int corr_rescore_launch(const CorrGeom &g, const CorrWorkspace &ws, int is_norm, int norm_input, int64_t *idx,
-                        float *val, cudaStream_t st) {
+// Exhaustive exact re-scan of the flagged (query, chunk) pairs: one block per list entry (grid-stride), warps
+// stride over the chunk's Ref patches.  Rare on real data (three candidates within ~1e-4 of each other in one
+// chunk, or exact ties), but it is what makes the candidate lists sufficient instead of "empirically enough".
+__global__ void __launch_bounds__(256) rescore_overflow_kernel(const float *__restrict__ pin, const float *__restrict__ pref,
+                                                               CorrGeom g, CorrChunkGeom cg, int nchunk, int is_norm,
+                                                               const CorrOverflow *__restrict__ ovf,
+                                                               const unsigned *__restrict__ ovf_count,
+                                                               int64_t *__restrict__ idx, float *__restrict__ val) {
+    __shared__ float s_best[8];
+    __shared__ int s_besti[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned count = *ovf_count;
+    for (unsigned e = blockIdx.x; e < count; e += gridDim.x) {
+        const CorrOverflow o = ovf[e];
+        const int b = o.query / g.NQ, q = o.query - b * g.NQ;
+        const float *pinb = pin + (size_t)b * g.h * g.w * g.Cp;
+        const float *prefb = pref + (size_t)b * g.hr * g.wr * g.Cp;
+        const int qp = ((q / g.gw) * g.s_in) * g.w + (q % g.gw) * g.s_in;
+        float best = -INFINITY;
+        int besti = 0x7fffffff;
+        for (int c = 0; c < nchunk; ++c) {
+            if (!((o.chunks >> c) & 1u)) continue;
+            if (cg.mode == 0) {
+                const int r0 = c * cg.per, r1 = min(g.NR, r0 + cg.per);
+                for (int r = r0 + warp; r < r1; r += 8) {
+                    const int rp = ((r / g.rw) * g.s_ref) * g.wr + (r % g.rw) * g.s_ref;
+                    const float s = exact_score_warp(pinb, prefb, g, qp, rp, is_norm, lane);
+                    if (cand_better(s, r, best, besti)) { best = s; besti = r; }
+                }
+            } else {
+                const int t0 = c * cg.per, t1 = min(cg.n_rt, t0 + cg.per);
+                const int per_tile = cg.tile_rows * cg.tile_cols;
+                for (int sl = warp; sl < (t1 - t0) * per_tile; sl += 8) {
+                    const int rt = t0 + sl / per_tile, w = sl % per_tile;
+                    const int ry = (rt / cg.rt_x) * cg.tile_rows + w / cg.tile_cols;
+                    const int rx = (rt % cg.rt_x) * cg.tile_cols + w % cg.tile_cols;
+                    if (ry >= g.rh || rx >= g.rw) continue;
+                    const int r = ry * g.rw + rx;
+                    const float s = exact_score_warp(pinb, prefb, g, qp, (ry * g.s_ref) * g.wr + rx * g.s_ref, is_norm, lane);
+                    if (cand_better(s, r, best, besti)) { best = s; besti = r; }
+                }
+            }
+        }
+        if (lane == 0) { s_best[warp] = best; s_besti[warp] = besti; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            // merge with what the windowed pass found in the other chunks (raw scores on both sides)
+            float bb = val[o.query];
+            int bi = (int)idx[o.query];
+            if (bi < 0) { bb = -INFINITY; bi = 0x7fffffff; }
+            for (int w = 0; w < 8; ++w)
+                if (s_besti[w] != 0x7fffffff && cand_better(s_best[w], s_besti[w], bb, bi)) { bb = s_best[w]; bi = s_besti[w]; }
+            idx[o.query] = bi;
+            val[o.query] = bb;
+        }
+        __syncthreads();
+    }
+}
+
+// val /= ||P_query|| + 1e-5 (ref_map_util.py:78-84), idx -1 (no candidate at all) -> 0
+__global__ void __launch_bounds__(256) rescore_finish_kernel(const float *__restrict__ ss_in, CorrGeom g, int norm_input,
+                                                             int64_t *__restrict__ idx, float *__restrict__ val) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (q >= g.NQ) return;
+    const size_t o = (size_t)b * g.NQ + q;
+    if (idx[o] < 0) idx[o] = 0;
+    if (norm_input) {
+        const int qy = (q / g.gw) * g.s_in, qx = (q % g.gw) * g.s_in;
+        const float *s = ss_in + (size_t)b * g.h * g.w;
+        double acc = 0.0;
+        for (int dy = 0; dy < g.patch; ++dy)
+            for (int dx = 0; dx < g.patch; ++dx) acc += (double)s[(qy + dy) * g.w + qx + dx];
+        val[o] = val[o] / ((float)sqrt(acc) + 1e-5f);
+    }
+}
+
+int corr_rescore_launch(const CorrGeom &g, const CorrWorkspace &ws, const CorrChunkGeom &cg, float window_coef,
+                        int is_norm, int norm_input, int64_t *idx, float *val, cudaStream_t st) {
     dim3 grid(ceil_div(g.NQ, 8), g.B);
-    rescore_kernel<<<grid, 256, 0, st>>>(ws.p32_in, ws.p32_ref, ws.part, g, ws.nchunk, is_norm, norm_input, idx, val);
+    rescore_kernel<<<grid, 256, 0, st>>>(ws.p32_in, ws.p32_ref, ws.part, g, ws.nchunk, window_coef, ws.max_pn_bits,
+                                         is_norm, norm_input, idx, val, ws.ovf, ws.ovf_count);
     C2M_LAUNCH_CHECK("rescore_kernel");
+    rescore_overflow_kernel<<<296, 256, 0, st>>>(ws.p32_in, ws.p32_ref, g, cg, ws.nchunk, is_norm, ws.ovf, ws.ovf_count,
+                                                 idx, val);
+    C2M_LAUNCH_CHECK("rescore_overflow_kernel");
+    rescore_finish_kernel<<<dim3(ceil_div(g.NQ, 256), g.B), 256, 0, st>>>(ws.ss_in, g, norm_input, idx, val);
+    C2M_LAUNCH_CHECK("rescore_finish_kernel");
     return C2M_OK;
 }
 

@@ -10,7 +10,9 @@
 //                            K-major no-swizzle core-matrix layout with rows 16 B apart.
 //   ss    [B][HW]            fp32 per-pixel sum of squares of p32 (for the patch norms).
 //   rinv  [B][NR]            fp32 1 / (sqrt(sum_{patch} ss) + 1e-5)   (1 when !is_norm)
-//   part  [B][nchunk][NQ]    Candidate: approximate top-2 of each query over one Ref chunk.
+//   part  [B][nchunk][NQ]    Candidate: approximate top-2 of each query over one Ref chunk (nchunk <= 32).
+//   ovf   [B*NQ]             (query, chunk bit mask) of the (query, chunk) pairs whose top-2 list may be incomplete:
+//                            the exhaustive pass re-scans those chunks exactly (see corr_aux.cu).
 #pragma once
 #include "c2m_common.cuh"
 
@@ -31,14 +33,31 @@ struct CorrGeom {
     int NQ, NR;
 };
 
+constexpr int CORR_MAX_CHUNKS = 32;
+
+// how a chunk index maps to Ref patches (for the exhaustive fallback)
+struct CorrChunkGeom {
+    int mode;                // 0: contiguous Ref index ranges of `per` patches (generic search); 1: runs of `per` tiles
+    int per;
+    int n_rt, rt_x, tile_rows, tile_cols;    // mode 1: tile grid over the Ref patch grid
+};
+
+struct CorrOverflow {
+    int query;               // b * NQ + q
+    unsigned chunks;         // bit c: chunk c must be re-scanned
+};
+
 struct CorrWorkspace {
     float *p32_in, *p32_ref;
     __half *hi_in, *lo_in, *hi_ref, *lo_ref;
     float *ss_in, *ss_ref;
     float *rinv;
     Candidate *part;
+    CorrOverflow *ovf;       // [B*NQ] overflow list
     unsigned *amax_bits;     // [2]
     int *sexp;               // [2] scale exponents for (in, ref)
+    unsigned *ovf_count;     // [1] entries in ovf
+    unsigned *max_pn_bits;   // [1] max over Ref patches of ||P_ref|| (float bits) — window scale when !is_norm
     int nchunk;
     size_t total_bytes;
 };
@@ -62,8 +81,11 @@ int corr_rinv_launch(const CorrGeom &g, const CorrWorkspace &ws, int is_norm, cu
 int corr_search_generic_launch(const CorrGeom &g, const CorrWorkspace &ws, cudaStream_t st);
 int corr_search_umma_launch(const CorrGeom &g, const CorrWorkspace &ws, cudaStream_t st);
 bool corr_umma_supported(const CorrGeom &g);
-int corr_umma_pick_nchunk(const CorrGeom &g);
-int corr_rescore_launch(const CorrGeom &g, const CorrWorkspace &ws, int is_norm, int norm_input,
-                        int64_t *idx, float *val, cudaStream_t st);
+int corr_umma_pick_nchunk(const CorrGeom &g, int sms);
+void corr_umma_chunk_geom(const CorrGeom &g, int nchunk, CorrChunkGeom &cg);
+void corr_generic_chunk_geom(const CorrGeom &g, int nchunk, CorrChunkGeom &cg);
+// window_coef: rigorous bound on 2 x |approximate - exact score| per unit of ||P_query|| (see corr_aux.cu)
+int corr_rescore_launch(const CorrGeom &g, const CorrWorkspace &ws, const CorrChunkGeom &cg, float window_coef,
+                        int is_norm, int norm_input, int64_t *idx, float *val, cudaStream_t st);
 
 }  // namespace c2m

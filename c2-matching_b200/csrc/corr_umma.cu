@@ -4,24 +4,27 @@
 // (mmsr/models/archs/ref_map_util.py:54-76), which materialises a [n_ref, h', w'] score tensor
 // per chunk (2 x 2.09 GB per image at 160x160 maps).  Here no score ever reaches HBM.
 //
-// Formulation.  score(q,r) = sum_{tap in 3x3} sum_c in[q+tap][c] * ref[r+tap][c] is a GEMM with
-// K = 9*C whose A/B rows for tap (dy,dx) are the SAME pixel rows shifted by (dy,dx).  Each CTA
-// therefore stages, per 32-channel slice, one halo'd pixel block per side —
-//   A: (16+2) x (8+2) input pixels   B: (32+2) x (8+2) Ref pixels
-// — with one TMA box each into the tcgen05 K-major *no-swizzle* layout [octet][pixel][8 halfs]
-// (rows 16 B apart), and issues the 9 taps as 9 MMAs whose shared-memory descriptors differ only
-// in their start address (+ (dy*10+dx)*16 B).  8-row core-matrix groups are tile rows, so the
-// stride-byte-offset is the block row pitch (10 px * 16 B); the two K core matrices of a
-// UMMA_K=16 step are `octet pitch` apart (leading-byte-offset).  Operand traffic from L2 is 9x
-// lower than an im2col GEMM and nothing is re-laid-out in shared memory.
+// Formulation.  score(q,r) = sum_{dy,dx in 3x3} sum_c in[q+(dy,dx)][c] * ref[r+(dy,dx)][c].  The row taps go to
+// the tensor core, the column taps to the epilogue:
+//     V(p, s)     = sum_{dy} sum_c in[p+(dy,0)][c] * ref[s+(dy,0)][c]          GEMM, K = 3*C (a third of 9*C)
+//     score(q, r) = V(q, r) + V(q+(0,1), r+(0,1)) + V(q+(0,2), r+(0,2))        3-term diagonal sum
+// Pixel blocks are 16 columns wide on both sides (14 patch origins + 2 halo columns), stored by ONE TMA box per
+// operand half as [octet][row][16 px][8 halfs]: 16 px x 16 B = 256 B rows are contiguous, so M index m = 16*row + x
+// (query block: 8 rows -> M = 128) and N index n = 16*row + x (Ref block: 16 rows -> N = 256) are CONTIGUOUS pixel
+// runs in the tcgen05 K-major no-swizzle layout (8-pixel core-matrix groups 128 B apart = SBO, channel octets
+// one block apart = LBO), and the row tap dy is a +256 B start-address offset on both descriptors.
+// In the accumulator, lane m+dx / column n+dx hold V(q+(0,dx), r+(0,dx)): a warp's 32 lanes are exactly two
+// 16-px block rows, so the diagonal sum is two __shfl_down per score — no shared memory, no extra TMEM traffic.
+// Tile efficiency (14/16)^2 = 0.77, i.e. 2.3x fewer MMA cycles per score than issuing all nine taps.
 //
 // Precision.  Operands are split fp16 pairs of x*2^sexp (hi + lo, 22 mantissa bits); each K step
 // issues hi*hi + hi*lo + lo*hi into the same fp32 TMEM accumulator (M=128, N=256).  The scores
-// only RANK candidates: the epilogue keeps a top-2 per query and the exact rescoring kernel
-// (corr_aux.cu) decides, so tensor-core rounding cannot leak into the index map.
+// only RANK candidates: the epilogue keeps a top-2 per (query, Ref chunk) and the exact rescoring kernel
+// (corr_aux.cu) decides, so tensor-core rounding cannot leak into the index map; corr_aux.cu states the error
+// bound that sizes the rescoring window and the exhaustive fallback that makes the top-2 lists sufficient.
 //
 // CTA = 256 threads: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7
-// epilogue (one query row each, TMEM lane quarter = warp % 4).  3-stage smem ring (66.5 KB per
+// epilogue (TMEM lane quarter = warp % 4 = two query-block rows).  3-stage smem ring (56 KB per
 // stage), 2 x 256-column TMEM accumulators so the epilogue of Ref tile n overlaps the MMAs of
 // tile n+1.  Persistent: grid = #SMs, work item = (image, query tile, Ref chunk).
 #include "corr_internal.cuh"
@@ -30,24 +33,26 @@ namespace c2m {
 
 namespace {
 constexpr int PATCH = 3;
-constexpr int TQ_R = 16, TQ_C = 8;                 // query tile -> UMMA M = 128
-constexpr int TR_R = 32, TR_C = 8;                 // Ref tile   -> UMMA N = 256
-constexpr int AB_C = TQ_C + PATCH - 1;             // 10 block columns (both sides)
-constexpr int A_R = TQ_R + PATCH - 1;              // 18
-constexpr int B_R = TR_R + PATCH - 1;              // 34
+constexpr int BW = 16;                             // block width in pixels (both sides)
+constexpr int TV = BW - (PATCH - 1);               // 14 valid patch origins per block row
+constexpr int TQ_R = 8;                            // query block rows  -> UMMA M = 8 * 16 = 128
+constexpr int TR_R = 16;                           // Ref block rows    -> UMMA N = 16 * 16 = 256
+constexpr int A_R = TQ_R + PATCH - 1;              // 10 staged rows
+constexpr int B_R = TR_R + PATCH - 1;              // 18
 constexpr int KOCT = 4;                            // channel octets per stage (32 channels)
-constexpr int ROW_B = AB_C * 16;                   // 160 B block row pitch  (= SBO)
-constexpr int A_OCT_B = A_R * ROW_B;               // 2880 B octet pitch of A (= LBO)
-constexpr int B_OCT_B = B_R * ROW_B;               // 5440 B octet pitch of B (= LBO)
-constexpr int A_BYTES = KOCT * A_OCT_B;            // 11520
-constexpr int B_BYTES = KOCT * B_OCT_B;            // 21760
-constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);   // hi+lo of both sides = 66560
+constexpr int ROW_B = BW * 16;                     // 256 B block row pitch (= row-tap offset)
+constexpr int A_OCT_B = A_R * ROW_B;               // 2560 B octet pitch of A (= LBO)
+constexpr int B_OCT_B = B_R * ROW_B;               // 4608 B octet pitch of B (= LBO)
+constexpr int A_BYTES = KOCT * A_OCT_B;            // 10240
+constexpr int B_BYTES = KOCT * B_OCT_B;            // 18432
+constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);   // hi+lo of both sides = 57344
 constexpr int NSTAGE = 3;
-constexpr int UM = TQ_R * TQ_C, UN = TR_R * TR_C;  // 128, 256
+constexpr int UM = TQ_R * BW, UN = TR_R * BW;      // 128, 256
 constexpr int TMEM_COLS = 512;
-constexpr int SMEM_AUX = 2 * UN * 4 + 2 * UN * 4 + 128;   // rinv + ridx double buffers + barriers
+constexpr int SMEM_AUX = 2 * UN * 8 + 128;         // (scale, index) per column, double buffered, + barriers
 constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + SMEM_AUX + 1024;
 static_assert(A_BYTES % 128 == 0 && B_BYTES % 128 == 0, "TMA destinations must stay 128B aligned");
+static_assert(UM == 128 && UN == 256, "tile shape is tied to the UMMA instruction shape");
 
 struct UmmaParams {
     int B, C8;
@@ -66,9 +71,8 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap tm_in_hi, const __grid_cons
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *aux = smem + NSTAGE * STAGE_BYTES;
-    float *rs = reinterpret_cast<float *>(aux);                     // [2][UN]
-    int *ri = reinterpret_cast<int *>(aux + 2 * UN * 4);            // [2][UN]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(aux + 4 * UN * 4);
+    float2 *rcol = reinterpret_cast<float2 *>(aux);                 // [2][UN] (score scale, Ref index bits or -1)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(aux + 2 * UN * 8);
     uint64_t *full = bars, *empty = bars + NSTAGE, *tfull = bars + 2 * NSTAGE, *tempty = bars + 2 * NSTAGE + 2;
     uint32_t *tmem_base_p = reinterpret_cast<uint32_t *>(bars + 2 * NSTAGE + 4);
 
@@ -104,10 +108,10 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap tm_in_hi, const __grid_cons
             int stage = 0, phase = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const int chunk = item % p.nchunk, qt = (item / p.nchunk) % n_qt, b = item / (p.nchunk * n_qt);
-                const int qy0 = (qt / p.qt_x) * TQ_R, qx0 = (qt % p.qt_x) * TQ_C;
+                const int qy0 = (qt / p.qt_x) * TQ_R, qx0 = (qt % p.qt_x) * TV;
                 const int rt_b = chunk * p.rt_per_chunk, rt_e = min(n_rt, rt_b + p.rt_per_chunk);
                 for (int rt = rt_b; rt < rt_e; ++rt) {
-                    const int ry0 = (rt / p.rt_x) * TR_R, rx0 = (rt % p.rt_x) * TR_C;
+                    const int ry0 = (rt / p.rt_x) * TR_R, rx0 = (rt % p.rt_x) * TV;
                     for (int kc = 0; kc < n_kc; ++kc) {
                         mbar_wait(&empty[stage], phase ^ 1);
                         uint8_t *s = smem + stage * STAGE_BYTES;
@@ -137,19 +141,19 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap tm_in_hi, const __grid_cons
                         mbar_wait(&full[stage], phase);
                         tc_fence_after();
                         const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-                        const uint32_t a_hi = sa, a_lo = sa + A_BYTES, b_hi = sa + 2 * A_BYTES,
-                                       b_lo = sa + 2 * A_BYTES + B_BYTES;
+                        // descriptors of (row tap 0, k-step 0); every other MMA is a constant offset away
+                        const uint64_t dah0 = umma_smem_desc(sa, A_OCT_B, 128);
+                        const uint64_t dal0 = umma_smem_desc(sa + A_BYTES, A_OCT_B, 128);
+                        const uint64_t dbh0 = umma_smem_desc(sa + 2 * A_BYTES, B_OCT_B, 128);
+                        const uint64_t dbl0 = umma_smem_desc(sa + 2 * A_BYTES + B_BYTES, B_OCT_B, 128);
 #pragma unroll
-                        for (int tap = 0; tap < PATCH * PATCH; ++tap) {
-                            const uint32_t toff = ((tap / PATCH) * AB_C + tap % PATCH) * 16;
+                        for (int dy = 0; dy < PATCH; ++dy) {
 #pragma unroll
                             for (int j = 0; j < KOCT / 2; ++j) {
-                                const uint32_t ao = toff + j * 2 * A_OCT_B, bo = toff + j * 2 * B_OCT_B;
-                                const uint64_t dah = umma_smem_desc(a_hi + ao, A_OCT_B, ROW_B);
-                                const uint64_t dal = umma_smem_desc(a_lo + ao, A_OCT_B, ROW_B);
-                                const uint64_t dbh = umma_smem_desc(b_hi + bo, B_OCT_B, ROW_B);
-                                const uint64_t dbl = umma_smem_desc(b_lo + bo, B_OCT_B, ROW_B);
-                                umma_f16(d, dah, dbh, idesc, (kc | tap | j) != 0);
+                                const uint32_t ao = dy * ROW_B + j * 2 * A_OCT_B, bo = dy * ROW_B + j * 2 * B_OCT_B;
+                                const uint64_t dah = umma_desc_advance(dah0, ao), dal = umma_desc_advance(dal0, ao);
+                                const uint64_t dbh = umma_desc_advance(dbh0, bo), dbl = umma_desc_advance(dbl0, bo);
+                                umma_f16(d, dah, dbh, idesc, (kc | dy | j) != 0);
                                 umma_f16(d, dah, dbl, idesc, 1);
                                 umma_f16(d, dal, dbh, idesc, 1);
                             }
@@ -164,43 +168,52 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap tm_in_hi, const __grid_cons
         }
     } else if (warp >= 4) {
         // ================================ epilogue =========================================
-        const int e = threadIdx.x - 128;                    // 0..127 = query row m of the tile
+        const int e = threadIdx.x - 128;                    // 0..127 = accumulator row m = 16 * block row + block column
         const int quarter = warp & 3;
+        const int yy = e >> 4, xx = e & 15;
         const float sinv = ldexpf(1.f, -(sexp[0] + sexp[1]));
         int acc = 0, acc_phase = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int chunk = item % p.nchunk, qt = (item / p.nchunk) % n_qt, b = item / (p.nchunk * n_qt);
-            const int qy = (qt / p.qt_x) * TQ_R + e / TQ_C, qx = (qt % p.qt_x) * TQ_C + e % TQ_C;
+            const int qy = (qt / p.qt_x) * TQ_R + yy, qx = (qt % p.qt_x) * TV + xx;
             const int rt_b = chunk * p.rt_per_chunk, rt_e = min(n_rt, rt_b + p.rt_per_chunk);
             const float *rinvb = rinv + (size_t)b * p.NR;
             float v1 = -INFINITY, v2 = -INFINITY;
             int i1 = 0x7fffffff, i2 = 0x7fffffff;
             for (int rt = rt_b; rt < rt_e; ++rt) {
-                const int ry0 = (rt / p.rt_x) * TR_R, rx0 = (rt % p.rt_x) * TR_C;
-                float *rsb = rs + acc * UN;
-                int *rib = ri + acc * UN;
+                const int ry0 = (rt / p.rt_x) * TR_R, rx0 = (rt % p.rt_x) * TV;
+                float2 *rc = rcol + acc * UN;
 #pragma unroll
                 for (int k = 0; k < UN / 128; ++k) {
                     const int n = e + k * 128;
-                    const int ry = ry0 + n / TR_C, rx = rx0 + n % TR_C;
-                    const bool ok = ry < p.rh && rx < p.rw;
+                    const int uu = n >> 4, vv = n & 15;
+                    const int ry = ry0 + uu, rx = rx0 + vv;
+                    const bool ok = vv < TV && ry < p.rh && rx < p.rw;
                     const int r = ry * p.rw + rx;
-                    rsb[n] = ok ? rinvb[r] * sinv : 0.f;
-                    rib[n] = ok ? r : -1;
+                    rc[n] = make_float2(ok ? rinvb[r] * sinv : 0.f, __int_as_float(ok ? r : -1));
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 mbar_wait(&tfull[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * UN;
 #pragma unroll 1
-                for (int cc = 0; cc < UN / 32; ++cc) {
+                for (int cc = 0; cc < UN / 32; ++cc) {      // 32 columns = two Ref block rows
                     uint32_t reg[32];
                     tmem_ld_32x32(taddr + cc * 32, reg);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int r = rib[cc * 32 + j];
-                        if (r >= 0) cand_push(__uint_as_float(reg[j]) * rsb[cc * 32 + j], r, v1, i1, v2, i2);
+                    for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+                        for (int v = 0; v < TV; ++v) {
+                            const int j = hh * 16 + v;
+                            // column taps: lane m+dx, column n+dx hold V(q + (0,dx), r + (0,dx))
+                            const float t1 = __shfl_down_sync(0xffffffffu, __uint_as_float(reg[j + 1]), 1);
+                            const float t2 = __shfl_down_sync(0xffffffffu, __uint_as_float(reg[j + 2]), 2);
+                            const float sc = (__uint_as_float(reg[j]) + t1) + t2;
+                            const float2 c = rc[cc * 32 + j];
+                            const int r = __float_as_int(c.y);
+                            if (r >= 0) cand_push(sc * c.x, r, v1, i1, v2, i2);
+                        }
                     }
                 }
                 tc_fence_before();
@@ -208,7 +221,7 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap tm_in_hi, const __grid_cons
                 if (lane == 0) mbar_arrive(&tempty[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            if (qy < p.gh && qx < p.gw)
+            if (xx < TV && qy < p.gh && qx < p.gw)
                 part[((size_t)b * p.nchunk + chunk) * p.NQ + qy * p.gw + qx] =
                     Candidate{v1, i1 == 0x7fffffff ? -1 : i1, v2, i2 == 0x7fffffff ? -1 : i2};
         }
@@ -241,13 +254,13 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// map [B][C8][H][W][8] fp16 as a 4-D tensor (W*8, H, C8, B) with a (80, rows, KOCT, 1) box
+// map [B][C8][H][W][8] fp16 as a 4-D tensor (W*8, H, C8, B) with a (16 px * 8, rows, KOCT, 1) box
 static int make_map(CUtensorMap *m, const __half *base, int B, int C8, int H, int W, int rows) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return C2M_ERR_UNSUPPORTED; }
     cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)C8, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)C8 * H * W * 16};
-    cuuint32_t box[4] = {(cuuint32_t)AB_C * 8, (cuuint32_t)rows, (cuuint32_t)KOCT, 1};
+    cuuint32_t box[4] = {(cuuint32_t)BW * 8, (cuuint32_t)rows, (cuuint32_t)KOCT, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half *>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -257,20 +270,43 @@ static int make_map(CUtensorMap *m, const __half *base, int B, int C8, int H, in
 }
 
 bool corr_umma_supported(const CorrGeom &g) {
-    return g.patch == PATCH && g.s_in == 1 && g.s_ref == 1 && g.w >= AB_C && g.h >= A_R && g.wr >= AB_C &&
+    return g.patch == PATCH && g.s_in == 1 && g.s_ref == 1 && g.w >= BW && g.h >= A_R && g.wr >= BW &&
            g.hr >= B_R;
 }
 
-int corr_umma_pick_nchunk(const CorrGeom &g) {
-    const int n_qt = ceil_div(g.gh, TQ_R) * ceil_div(g.gw, TQ_C);
-    const int n_rt = ceil_div(g.rh, TR_R) * ceil_div(g.rw, TR_C);
-    int n = ceil_div(8 * 148, g.B * n_qt);
-    if (n > 16) n = 16;
-    if (n > n_rt) n = n_rt;
-    if (n < 1) n = 1;
-    // no empty chunks: chunks hold ceil(n_rt/n) tiles
-    const int per = ceil_div(n_rt, n);
-    return ceil_div(n_rt, per);
+void corr_umma_tiles(const CorrGeom &g, int &n_qt, int &n_rt) {
+    n_qt = ceil_div(g.gh, TQ_R) * ceil_div(g.gw, TV);
+    n_rt = ceil_div(g.rh, TR_R) * ceil_div(g.rw, TV);
+}
+
+// Ref chunks per query tile: the split that minimises (waves over the SMs) x (tiles per item + a fill / drain
+// allowance), so small problems (BASELINE config 3: 15 query tiles) still spread over all SMs.
+int corr_umma_pick_nchunk(const CorrGeom &g, int sms) {
+    int n_qt, n_rt;
+    corr_umma_tiles(g, n_qt, n_rt);
+    if (sms <= 0) sms = 148;
+    int best_n = 1;
+    double best_cost = 1e300;
+    for (int n = 1; n <= CORR_MAX_CHUNKS && n <= n_rt; ++n) {
+        const int per = ceil_div(n_rt, n);
+        const int n_eff = ceil_div(n_rt, per);
+        if (n_eff != n) continue;                      // no empty chunks
+        const long long items = (long long)g.B * n_qt * n;
+        const double waves = (double)((items + sms - 1) / sms);
+        const double cost = waves * (per + 0.35);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best_n = n; }
+    }
+    return best_n;
+}
+
+// chunk -> Ref tile range and tile -> Ref patch rectangle, for the exhaustive fallback of the rescoring pass
+void corr_umma_chunk_geom(const CorrGeom &g, int nchunk, CorrChunkGeom &cg) {
+    cg.mode = 1;
+    cg.rt_x = ceil_div(g.rw, TV);
+    cg.n_rt = cg.rt_x * ceil_div(g.rh, TR_R);
+    cg.per = ceil_div(cg.n_rt, nchunk);
+    cg.tile_rows = TR_R;
+    cg.tile_cols = TV;
 }
 
 int corr_search_umma_launch(const CorrGeom &g, const CorrWorkspace &ws, cudaStream_t st) {
@@ -285,8 +321,8 @@ int corr_search_umma_launch(const CorrGeom &g, const CorrWorkspace &ws, cudaStre
     UmmaParams p;
     p.B = g.B; p.C8 = C8;
     p.gh = g.gh; p.gw = g.gw; p.rh = g.rh; p.rw = g.rw;
-    p.qt_x = ceil_div(g.gw, TQ_C); p.qt_y = ceil_div(g.gh, TQ_R);
-    p.rt_x = ceil_div(g.rw, TR_C); p.rt_y = ceil_div(g.rh, TR_R);
+    p.qt_x = ceil_div(g.gw, TV); p.qt_y = ceil_div(g.gh, TQ_R);
+    p.rt_x = ceil_div(g.rw, TV); p.rt_y = ceil_div(g.rh, TR_R);
     p.nchunk = ws.nchunk;
     p.rt_per_chunk = ceil_div(p.rt_x * p.rt_y, ws.nchunk);
     p.NQ = g.NQ; p.NR = g.NR;
