@@ -81,6 +81,8 @@ static void carve(CorrWorkspace &ws, const CorrGeom &g, uint8_t *base) {
     ws.rinv = (float *)take((size_t)g.B * g.NR * 4);
     ws.part = (Candidate *)take((size_t)g.B * CORR_MAX_CHUNKS * g.NQ * sizeof(Candidate));
     ws.ovf = (CorrOverflow *)take((size_t)g.B * g.NQ * sizeof(CorrOverflow));
+    ws.best = (unsigned long long *)take((size_t)g.B * g.NQ * 8);
+    ws.qnorm = (float *)take((size_t)g.B * g.NQ * 4);
     ws.amax_bits = (unsigned *)take(256);            // zeroed at the start of every call
     ws.sexp = (int *)(ws.amax_bits ? ws.amax_bits + 8 : nullptr);
     ws.ovf_count = ws.amax_bits ? ws.amax_bits + 16 : nullptr;

@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(256) search_generic_kernel(const float *__rest
     __shared__ int qpix[GS_T];
     __shared__ int rpix[GS_T];
     __shared__ float rsc[GS_T];
-    __shared__ Candidate red[GS_T][16];
+    __shared__ Candidate red[GS_T][16];          // 32 KB
 
     const int b = blockIdx.z, chunk = blockIdx.y;
     const int q0 = blockIdx.x * GS_T;
@@ -197,10 +197,10 @@ __global__ void __launch_bounds__(256) search_generic_kernel(const float *__rest
     const int per = ceil_div(ceil_div(g.NR, GS_T), nchunk) * GS_T;
     const int r_begin = chunk * per, r_end = min(g.NR, r_begin + per);
 
-    float v1[4], v2[4];
-    int i1[4], i2[4];
+    float cv[4][CORR_TOPK];
+    int ci[4][CORR_TOPK];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { v1[i] = v2[i] = -INFINITY; i1[i] = i2[i] = 0x7fffffff; }
+    for (int i = 0; i < 4; ++i) cand_init(cv[i], ci[i]);
 
     const int lrow = t >> 1 & 63, lhalf = t & 1;     // loader: threads 0..127 -> A, 128..255 -> B
     for (int r0 = r_begin; r0 < r_end; r0 += GS_T) {
@@ -254,24 +254,30 @@ __global__ void __launch_bounds__(256) search_generic_kernel(const float *__rest
             if (r < r_end) {
                 const float sc = rsc[tx * 4 + j];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) cand_push(acc[i][j] * sc, r, v1[i], i1[i], v2[i], i2[i]);
+                for (int i = 0; i < 4; ++i) cand_push(acc[i][j] * sc, r, cv[i], ci[i]);
             }
         }
     }
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 4; ++i) red[ty * 4 + i][tx] = Candidate{v1[i], i1[i], v2[i], i2[i]};
+    for (int i = 0; i < 4; ++i) {
+        Candidate c;
+#pragma unroll
+        for (int k = 0; k < CORR_TOPK; ++k) { c.v[k] = cv[i][k]; c.i[k] = ci[i][k]; }
+        red[ty * 4 + i][tx] = c;
+    }
     __syncthreads();
     if (t < GS_T && q0 + t < g.NQ) {
-        float a1 = -INFINITY, a2 = -INFINITY;
-        int j1 = 0x7fffffff, j2 = 0x7fffffff;
+        float av[CORR_TOPK];
+        int ai[CORR_TOPK];
+        cand_init(av, ai);
         for (int k = 0; k < 16; ++k) {
             const Candidate c = red[t][k];
-            if (c.i1 != 0x7fffffff) cand_push(c.v1, c.i1, a1, j1, a2, j2);
-            if (c.i2 != 0x7fffffff) cand_push(c.v2, c.i2, a1, j1, a2, j2);
+#pragma unroll
+            for (int j = 0; j < CORR_TOPK; ++j)
+                if (c.i[j] != 0x7fffffff) cand_push(c.v[j], c.i[j], av, ai);
         }
-        part[((size_t)b * nchunk + chunk) * g.NQ + q0 + t] =
-            Candidate{a1, j1 == 0x7fffffff ? -1 : j1, a2, j2 == 0x7fffffff ? -1 : j2};
+        part[((size_t)b * nchunk + chunk) * g.NQ + q0 + t] = cand_pack(av, ai);
     }
 }
 
@@ -306,28 +312,43 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// exact score of (query pixel qp, Ref pixel rp), computed by one warp; every lane returns it
+// exact score of (query pixel qp, Ref pixel rp), computed by one warp; every lane returns it.  Rows are read
+// as float4 (Cp is a multiple of 8) with the tap / channel loops unrolled so that several loads are in flight.
 __device__ __forceinline__ float exact_score_warp(const float *__restrict__ pinb, const float *__restrict__ prefb,
                                                   const CorrGeom &g, int qp, int rp, int is_norm, int lane) {
     const int taps = g.patch * g.patch;
     float denom = 1.f;
     if (is_norm) {
         double ss = 0.0;
+#pragma unroll 3
         for (int tap = 0; tap < taps; ++tap) {
             const float *row = prefb + (size_t)(rp + (tap / g.patch) * g.wr + tap % g.patch) * g.Cp;
-            for (int c = lane; c < g.Cp; c += 32) ss += (double)row[c] * (double)row[c];
+#pragma unroll 2
+            for (int c = lane * 4; c < g.Cp; c += 128) {
+                const float4 v = *reinterpret_cast<const float4 *>(row + c);
+                ss += (double)v.x * (double)v.x;
+                ss += (double)v.y * (double)v.y;
+                ss += (double)v.z * (double)v.z;
+                ss += (double)v.w * (double)v.w;
+            }
         }
         ss = warp_sum(ss);
         denom = (float)sqrt(ss) + 1e-5f;
     }
     double acc = 0.0;
+#pragma unroll 3
     for (int tap = 0; tap < taps; ++tap) {
         const int dy = tap / g.patch, dx = tap % g.patch;
         const float *rrow = prefb + (size_t)(rp + dy * g.wr + dx) * g.Cp;
         const float *qrow = pinb + (size_t)(qp + dy * g.w + dx) * g.Cp;
-        for (int c = lane; c < g.Cp; c += 32) {
-            const float pn = is_norm ? __fdiv_rn(rrow[c], denom) : rrow[c];
-            acc += (double)qrow[c] * (double)pn;
+#pragma unroll 2
+        for (int c = lane * 4; c < g.Cp; c += 128) {
+            const float4 rv = *reinterpret_cast<const float4 *>(rrow + c);
+            const float4 qv = *reinterpret_cast<const float4 *>(qrow + c);
+            acc += (double)qv.x * (double)(is_norm ? __fdiv_rn(rv.x, denom) : rv.x);
+            acc += (double)qv.y * (double)(is_norm ? __fdiv_rn(rv.y, denom) : rv.y);
+            acc += (double)qv.z * (double)(is_norm ? __fdiv_rn(rv.z, denom) : rv.z);
+            acc += (double)qv.w * (double)(is_norm ? __fdiv_rn(rv.w, denom) : rv.w);
         }
     }
     return (float)warp_sum(acc);
@@ -335,9 +356,15 @@ __device__ __forceinline__ float exact_score_warp(const float *__restrict__ pinb
 
 __device__ __forceinline__ double query_patch_ss(const float *__restrict__ pinb, const CorrGeom &g, int qp, int lane) {
     double ssq = 0.0;
+#pragma unroll 3
     for (int tap = 0; tap < g.patch * g.patch; ++tap) {
         const float *row = pinb + (size_t)(qp + (tap / g.patch) * g.w + tap % g.patch) * g.Cp;
-        for (int c = lane; c < g.Cp; c += 32) ssq += (double)row[c] * (double)row[c];
+#pragma unroll 2
+        for (int c = lane * 4; c < g.Cp; c += 128) {
+            const float4 v = *reinterpret_cast<const float4 *>(row + c);
+            ssq += (double)v.x * (double)v.x + (double)v.y * (double)v.y;
+            ssq += (double)v.z * (double)v.z + (double)v.w * (double)v.w;
+        }
     }
     return warp_sum(ssq);
 }
@@ -345,8 +372,8 @@ __device__ __forceinline__ double query_patch_ss(const float *__restrict__ pinb,
 __global__ void __launch_bounds__(256) rescore_kernel(const float *__restrict__ pin, const float *__restrict__ pref,
                                                       const Candidate *__restrict__ part, CorrGeom g, int nchunk,
                                                       float window_coef, const unsigned *__restrict__ max_pn_bits,
-                                                      int is_norm, int norm_input, int64_t *__restrict__ idx,
-                                                      float *__restrict__ val, CorrOverflow *__restrict__ ovf,
+                                                      int is_norm, unsigned long long *__restrict__ best_out,
+                                                      float *__restrict__ qnorm, CorrOverflow *__restrict__ ovf,
                                                       unsigned *__restrict__ ovf_count) {
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -356,85 +383,89 @@ __global__ void __launch_bounds__(256) rescore_kernel(const float *__restrict__ 
     const float *prefb = pref + (size_t)b * g.hr * g.wr * g.Cp;
     const int qp = ((q / g.gw) * g.s_in) * g.w + (q % g.gw) * g.s_in;
 
-    // candidates: slot c = 2 * chunk + {0: best, 1: second}; lane l holds slots l and l + 32 (nchunk <= 32)
-    float cv[2];
-    int ci[2];
+    // candidates: slot = CORR_TOPK * chunk + rank; lane l holds slots l, l + 32, l + 64, l + 96 (nchunk <= 32)
+    float cv[CORR_TOPK];
+    int ci[CORR_TOPK];
+    float vmax = -INFINITY;
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < CORR_TOPK; ++k) {
         const int slot = lane + 32 * k;
         cv[k] = -INFINITY;
         ci[k] = -1;
-        if (slot < 2 * nchunk) {
-            const Candidate c = part[((size_t)b * nchunk + (slot >> 1)) * g.NQ + q];
-            cv[k] = (slot & 1) ? c.v2 : c.v1;
-            ci[k] = (slot & 1) ? c.i2 : c.i1;
+        if (slot < CORR_TOPK * nchunk) {
+            const Candidate *c = part + ((size_t)b * nchunk + slot / CORR_TOPK) * g.NQ + q;
+            cv[k] = c->v[slot % CORR_TOPK];
+            ci[k] = c->i[slot % CORR_TOPK];
             if (ci[k] < 0) cv[k] = -INFINITY;
         }
+        vmax = fmaxf(vmax, cv[k]);
     }
-    float vmax = fmaxf(cv[0], cv[1]);
 #pragma unroll
     for (int o = 16; o; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
 
     // window = 2E: proportional to the query patch norm (and to the largest Ref patch norm when scores are raw)
-    const double ssq = query_patch_ss(pinb, g, qp, lane);
-    const float qn = (float)sqrt(ssq);
+    const float qn = (float)sqrt(query_patch_ss(pinb, g, qp, lane));
     const float window = window_coef * qn * (is_norm ? 1.f : __uint_as_float(*max_pn_bits)) + 1e-30f;
     const float thr = vmax - window;
 
-    // chunks whose SECOND entry is inside the window may hide further candidates -> exhaustive re-scan
+    // chunks whose LAST list entry is inside the window may hide further candidates -> exhaustive re-scan
     unsigned ovf_mask = 0;
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < CORR_TOPK; ++k) {
         const int slot = lane + 32 * k;
-        const bool hit = (slot & 1) && ci[k] >= 0 && cv[k] >= thr;
+        const bool hit = (slot % CORR_TOPK) == CORR_TOPK - 1 && ci[k] >= 0 && cv[k] >= thr;
         unsigned m = __ballot_sync(0xffffffffu, hit);
         while (m) {
             const int l = __ffs(m) - 1;
             m &= m - 1;
-            ovf_mask |= 1u << ((l + 32 * k) >> 1);
+            ovf_mask |= 1u << ((l + 32 * k) / CORR_TOPK);
         }
     }
 
     float best = -INFINITY;
     int besti = 0x7fffffff;
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < CORR_TOPK; ++k) {
         unsigned sel = __ballot_sync(0xffffffffu, ci[k] >= 0 && cv[k] >= thr);
         while (sel) {
             const int src = __ffs(sel) - 1;
             sel &= sel - 1;
             const int r = __shfl_sync(0xffffffffu, ci[k], src);
-            if ((ovf_mask >> ((src + 32 * k) >> 1)) & 1u) continue;      // the re-scan covers this chunk anyway
+            if ((ovf_mask >> ((src + 32 * k) / CORR_TOPK)) & 1u) continue;      // the re-scan covers this chunk anyway
             const int rp = ((r / g.rw) * g.s_ref) * g.wr + (r % g.rw) * g.s_ref;
             const float s = exact_score_warp(pinb, prefb, g, qp, rp, is_norm, lane);
             if (cand_better(s, r, best, besti)) { best = s; besti = r; }
         }
     }
     if (lane == 0) {
-        // raw best score; rescore_overflow_kernel / finish_kernel apply the input-norm division afterwards
-        idx[(size_t)b * g.NQ + q] = besti == 0x7fffffff ? -1 : besti;
-        val[(size_t)b * g.NQ + q] = best;
+        const size_t o = (size_t)b * g.NQ + q;
+        best_out[o] = besti == 0x7fffffff ? 0ull : best_key(best, besti);     // 0 sorts below every real key
+        qnorm[o] = qn;
         if (ovf_mask) {
             const unsigned n = atomicAdd(ovf_count, 1u);
-            ovf[n] = CorrOverflow{b * g.NQ + q, ovf_mask};           // capacity B * NQ: one entry per query at most
+            ovf[n] = CorrOverflow{(int)o, ovf_mask};               // capacity B * NQ: one entry per query at most
         }
     }
 }
 
-// Exhaustive exact re-scan of the flagged (query, chunk) pairs: one block per list entry (grid-stride), warps
-// stride over the chunk's Ref patches.  Rare on real data (three candidates within ~1e-4 of each other in one
-// chunk, or exact ties), but it is what makes the candidate lists sufficient instead of "empirically enough".
+// Exhaustive exact re-scan of the flagged (query, chunk) pairs.  Each list entry is cut into OVF_SPLIT slices of
+// the flagged chunks' Ref patches; a block takes (entry, slice) work items grid-stride, its warps stride over the
+// slice, and the result is merged into `best` with a 64-bit atomicMax on the packed (score, index) key.  With top-4
+// lists this runs for a handful of queries per batch on real data (four candidates within ~1e-4 of each other in
+// one chunk, or exact ties), but it is what makes the candidate lists sufficient instead of "empirically enough".
+constexpr int OVF_SPLIT = 64;
+
 __global__ void __launch_bounds__(256) rescore_overflow_kernel(const float *__restrict__ pin, const float *__restrict__ pref,
                                                                CorrGeom g, CorrChunkGeom cg, int nchunk, int is_norm,
                                                                const CorrOverflow *__restrict__ ovf,
                                                                const unsigned *__restrict__ ovf_count,
-                                                               int64_t *__restrict__ idx, float *__restrict__ val) {
-    __shared__ float s_best[8];
-    __shared__ int s_besti[8];
+                                                               unsigned long long *__restrict__ best_out) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned count = *ovf_count;
-    for (unsigned e = blockIdx.x; e < count; e += gridDim.x) {
-        const CorrOverflow o = ovf[e];
+    const int per_tile = cg.tile_rows * cg.tile_cols;
+    for (unsigned wi = blockIdx.x; wi < count * OVF_SPLIT; wi += gridDim.x) {
+        const CorrOverflow o = ovf[wi / OVF_SPLIT];
+        const int part_i = wi % OVF_SPLIT;
         const int b = o.query / g.NQ, q = o.query - b * g.NQ;
         const float *pinb = pin + (size_t)b * g.h * g.w * g.Cp;
         const float *prefb = pref + (size_t)b * g.hr * g.wr * g.Cp;
@@ -443,70 +474,55 @@ __global__ void __launch_bounds__(256) rescore_overflow_kernel(const float *__re
         int besti = 0x7fffffff;
         for (int c = 0; c < nchunk; ++c) {
             if (!((o.chunks >> c) & 1u)) continue;
-            if (cg.mode == 0) {
-                const int r0 = c * cg.per, r1 = min(g.NR, r0 + cg.per);
-                for (int r = r0 + warp; r < r1; r += 8) {
-                    const int rp = ((r / g.rw) * g.s_ref) * g.wr + (r % g.rw) * g.s_ref;
-                    const float s = exact_score_warp(pinb, prefb, g, qp, rp, is_norm, lane);
-                    if (cand_better(s, r, best, besti)) { best = s; besti = r; }
-                }
-            } else {
-                const int t0 = c * cg.per, t1 = min(cg.n_rt, t0 + cg.per);
-                const int per_tile = cg.tile_rows * cg.tile_cols;
-                for (int sl = warp; sl < (t1 - t0) * per_tile; sl += 8) {
-                    const int rt = t0 + sl / per_tile, w = sl % per_tile;
+            // slots of chunk c: Ref indices (mode 0) or (tile, position) pairs (mode 1); this block's slice of them
+            const int n_slots = cg.mode == 0 ? min(g.NR, (c + 1) * cg.per) - c * cg.per
+                                             : (min(cg.n_rt, (c + 1) * cg.per) - c * cg.per) * per_tile;
+            const int s0 = (int)((long long)n_slots * part_i / OVF_SPLIT), s1 = (int)((long long)n_slots * (part_i + 1) / OVF_SPLIT);
+            for (int sl = s0 + warp; sl < s1; sl += 8) {
+                int r;
+                if (cg.mode == 0) {
+                    r = c * cg.per + sl;
+                } else {
+                    const int rt = c * cg.per + sl / per_tile, w = sl % per_tile;
                     const int ry = (rt / cg.rt_x) * cg.tile_rows + w / cg.tile_cols;
                     const int rx = (rt % cg.rt_x) * cg.tile_cols + w % cg.tile_cols;
                     if (ry >= g.rh || rx >= g.rw) continue;
-                    const int r = ry * g.rw + rx;
-                    const float s = exact_score_warp(pinb, prefb, g, qp, (ry * g.s_ref) * g.wr + rx * g.s_ref, is_norm, lane);
-                    if (cand_better(s, r, best, besti)) { best = s; besti = r; }
+                    r = ry * g.rw + rx;
                 }
+                const int rp = ((r / g.rw) * g.s_ref) * g.wr + (r % g.rw) * g.s_ref;
+                const float s = exact_score_warp(pinb, prefb, g, qp, rp, is_norm, lane);
+                if (cand_better(s, r, best, besti)) { best = s; besti = r; }
             }
         }
-        if (lane == 0) { s_best[warp] = best; s_besti[warp] = besti; }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            // merge with what the windowed pass found in the other chunks (raw scores on both sides)
-            float bb = val[o.query];
-            int bi = (int)idx[o.query];
-            if (bi < 0) { bb = -INFINITY; bi = 0x7fffffff; }
-            for (int w = 0; w < 8; ++w)
-                if (s_besti[w] != 0x7fffffff && cand_better(s_best[w], s_besti[w], bb, bi)) { bb = s_best[w]; bi = s_besti[w]; }
-            idx[o.query] = bi;
-            val[o.query] = bb;
-        }
-        __syncthreads();
+        if (lane == 0 && besti != 0x7fffffff) atomicMax(best_out + o.query, best_key(best, besti));
     }
 }
 
-// val /= ||P_query|| + 1e-5 (ref_map_util.py:78-84), idx -1 (no candidate at all) -> 0
-__global__ void __launch_bounds__(256) rescore_finish_kernel(const float *__restrict__ ss_in, CorrGeom g, int norm_input,
+// unpack the winner; val /= ||P_query|| + 1e-5 when norm_input (ref_map_util.py:78-84)
+__global__ void __launch_bounds__(256) rescore_finish_kernel(const unsigned long long *__restrict__ best,
+                                                             const float *__restrict__ qnorm, int n, int norm_input,
                                                              int64_t *__restrict__ idx, float *__restrict__ val) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
-    if (q >= g.NQ) return;
-    const size_t o = (size_t)b * g.NQ + q;
-    if (idx[o] < 0) idx[o] = 0;
-    if (norm_input) {
-        const int qy = (q / g.gw) * g.s_in, qx = (q % g.gw) * g.s_in;
-        const float *s = ss_in + (size_t)b * g.h * g.w;
-        double acc = 0.0;
-        for (int dy = 0; dy < g.patch; ++dy)
-            for (int dx = 0; dx < g.patch; ++dx) acc += (double)s[(qy + dy) * g.w + qx + dx];
-        val[o] = val[o] / ((float)sqrt(acc) + 1e-5f);
-    }
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n) return;
+    const unsigned long long k = best[o];
+    float s = -INFINITY;
+    int r = 0;
+    if (k != 0ull) best_unkey(k, s, r);
+    idx[o] = r;
+    val[o] = norm_input ? s / (qnorm[o] + 1e-5f) : s;
 }
 
 int corr_rescore_launch(const CorrGeom &g, const CorrWorkspace &ws, const CorrChunkGeom &cg, float window_coef,
                         int is_norm, int norm_input, int64_t *idx, float *val, cudaStream_t st) {
     dim3 grid(ceil_div(g.NQ, 8), g.B);
     rescore_kernel<<<grid, 256, 0, st>>>(ws.p32_in, ws.p32_ref, ws.part, g, ws.nchunk, window_coef, ws.max_pn_bits,
-                                         is_norm, norm_input, idx, val, ws.ovf, ws.ovf_count);
+                                         is_norm, ws.best, ws.qnorm, ws.ovf, ws.ovf_count);
     C2M_LAUNCH_CHECK("rescore_kernel");
-    rescore_overflow_kernel<<<296, 256, 0, st>>>(ws.p32_in, ws.p32_ref, g, cg, ws.nchunk, is_norm, ws.ovf, ws.ovf_count,
-                                                 idx, val);
+    rescore_overflow_kernel<<<592, 256, 0, st>>>(ws.p32_in, ws.p32_ref, g, cg, ws.nchunk, is_norm, ws.ovf, ws.ovf_count,
+                                                 ws.best);
     C2M_LAUNCH_CHECK("rescore_overflow_kernel");
-    rescore_finish_kernel<<<dim3(ceil_div(g.NQ, 256), g.B), 256, 0, st>>>(ws.ss_in, g, norm_input, idx, val);
+    const int n = g.B * g.NQ;
+    rescore_finish_kernel<<<ceil_div(n, 256), 256, 0, st>>>(ws.best, ws.qnorm, n, norm_input, idx, val);
     C2M_LAUNCH_CHECK("rescore_finish_kernel");
     return C2M_OK;
 }

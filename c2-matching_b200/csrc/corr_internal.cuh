@@ -10,7 +10,7 @@
 //                            K-major no-swizzle core-matrix layout with rows 16 B apart.
 //   ss    [B][HW]            fp32 per-pixel sum of squares of p32 (for the patch norms).
 //   rinv  [B][NR]            fp32 1 / (sqrt(sum_{patch} ss) + 1e-5)   (1 when !is_norm)
-//   part  [B][nchunk][NQ]    Candidate: approximate top-2 of each query over one Ref chunk (nchunk <= 32).
+//   part  [B][nchunk][NQ]    Candidate: approximate top-4 of each query over one Ref chunk (nchunk <= 32).
 //   ovf   [B*NQ]             (query, chunk bit mask) of the (query, chunk) pairs whose top-2 list may be incomplete:
 //                            the exhaustive pass re-scans those chunks exactly (see corr_aux.cu).
 #pragma once
@@ -18,11 +18,10 @@
 
 namespace c2m {
 
+constexpr int CORR_TOPK = 4;      // candidates kept per (query, Ref chunk) by the searches
 struct __align__(16) Candidate {
-    float v1;
-    int i1;
-    float v2;
-    int i2;
+    float v[CORR_TOPK];           // approximate scores, best first
+    int i[CORR_TOPK];             // Ref patch indices (-1 = empty slot)
 };
 
 struct CorrGeom {
@@ -54,6 +53,8 @@ struct CorrWorkspace {
     float *rinv;
     Candidate *part;
     CorrOverflow *ovf;       // [B*NQ] overflow list
+    unsigned long long *best;   // [B*NQ] packed (exact score, index) of the best candidate so far (best_key)
+    float *qnorm;            // [B*NQ] ||P_query|| (exact, deterministic)
     unsigned *amax_bits;     // [2]
     int *sexp;               // [2] scale exponents for (in, ref)
     unsigned *ovf_count;     // [1] entries in ovf
@@ -66,12 +67,46 @@ struct CorrWorkspace {
 __device__ __forceinline__ bool cand_better(float s, int r, float v, int i) {
     return s > v || (s == v && r < i);
 }
-__device__ __forceinline__ void cand_push(float s, int r, float &v1, int &i1, float &v2, int &i2) {
-    if (cand_better(s, r, v1, i1)) {
-        v2 = v1; i2 = i1; v1 = s; i1 = r;
-    } else if (cand_better(s, r, v2, i2)) {
-        v2 = s; i2 = r;
+// sorted top-4 insert; the common case (not better than the 4th) costs one lexicographic compare
+__device__ __forceinline__ void cand_push(float s, int r, float (&v)[CORR_TOPK], int (&i)[CORR_TOPK]) {
+    if (!cand_better(s, r, v[3], i[3])) return;
+    if (cand_better(s, r, v[2], i[2])) {
+        v[3] = v[2]; i[3] = i[2];
+        if (cand_better(s, r, v[1], i[1])) {
+            v[2] = v[1]; i[2] = i[1];
+            if (cand_better(s, r, v[0], i[0])) {
+                v[1] = v[0]; i[1] = i[0]; v[0] = s; i[0] = r;
+            } else {
+                v[1] = s; i[1] = r;
+            }
+        } else {
+            v[2] = s; i[2] = r;
+        }
+    } else {
+        v[3] = s; i[3] = r;
     }
+}
+__device__ __forceinline__ void cand_init(float (&v)[CORR_TOPK], int (&i)[CORR_TOPK]) {
+#pragma unroll
+    for (int k = 0; k < CORR_TOPK; ++k) { v[k] = -INFINITY; i[k] = 0x7fffffff; }
+}
+__device__ __forceinline__ Candidate cand_pack(const float (&v)[CORR_TOPK], const int (&i)[CORR_TOPK]) {
+    Candidate c;
+#pragma unroll
+    for (int k = 0; k < CORR_TOPK; ++k) { c.v[k] = v[k]; c.i[k] = i[k] == 0x7fffffff ? -1 : i[k]; }
+    return c;
+}
+
+// (score, index) packed so that an unsigned 64-bit max is the lexicographic "better": larger score, then LOWER index
+__device__ __forceinline__ unsigned long long best_key(float s, int r) {
+    const unsigned b = __float_as_uint(s);
+    const unsigned ord = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    return ((unsigned long long)ord << 32) | (unsigned long long)(0xffffffffu - (unsigned)r);
+}
+__device__ __forceinline__ void best_unkey(unsigned long long k, float &s, int &r) {
+    const unsigned ord = (unsigned)(k >> 32);
+    s = __uint_as_float((ord & 0x80000000u) ? (ord & 0x7fffffffu) : ~ord);
+    r = (int)(0xffffffffu - (unsigned)(k & 0xffffffffu));
 }
 
 int corr_prep_launch(const float *x, int B, int C, int Cp, int HW, int l2norm, int map_slot,

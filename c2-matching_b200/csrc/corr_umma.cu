@@ -19,9 +19,9 @@
 //
 // Precision.  Operands are split fp16 pairs of x*2^sexp (hi + lo, 22 mantissa bits); each K step
 // issues hi*hi + hi*lo + lo*hi into the same fp32 TMEM accumulator (M=128, N=256).  The scores
-// only RANK candidates: the epilogue keeps a top-2 per (query, Ref chunk) and the exact rescoring kernel
+// only RANK candidates: the epilogue keeps a top-4 per (query, Ref chunk) and the exact rescoring kernel
 // (corr_aux.cu) decides, so tensor-core rounding cannot leak into the index map; corr_aux.cu states the error
-// bound that sizes the rescoring window and the exhaustive fallback that makes the top-2 lists sufficient.
+// bound that sizes the rescoring window and the exhaustive fallback that makes the top-4 lists sufficient.
 //
 // CTA = 256 threads: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7
 // epilogue (TMEM lane quarter = warp % 4 = two query-block rows).  3-stage smem ring (56 KB per
@@ -178,8 +178,9 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap tm_in_hi, const __grid_cons
             const int qy = (qt / p.qt_x) * TQ_R + yy, qx = (qt % p.qt_x) * TV + xx;
             const int rt_b = chunk * p.rt_per_chunk, rt_e = min(n_rt, rt_b + p.rt_per_chunk);
             const float *rinvb = rinv + (size_t)b * p.NR;
-            float v1 = -INFINITY, v2 = -INFINITY;
-            int i1 = 0x7fffffff, i2 = 0x7fffffff;
+            float cv[CORR_TOPK];
+            int ci[CORR_TOPK];
+            cand_init(cv, ci);
             for (int rt = rt_b; rt < rt_e; ++rt) {
                 const int ry0 = (rt / p.rt_x) * TR_R, rx0 = (rt % p.rt_x) * TV;
                 float2 *rc = rcol + acc * UN;
@@ -212,7 +213,7 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap tm_in_hi, const __grid_cons
                             const float sc = (__uint_as_float(reg[j]) + t1) + t2;
                             const float2 c = rc[cc * 32 + j];
                             const int r = __float_as_int(c.y);
-                            if (r >= 0) cand_push(sc * c.x, r, v1, i1, v2, i2);
+                            if (r >= 0) cand_push(sc * c.x, r, cv, ci);
                         }
                     }
                 }
@@ -222,8 +223,7 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap tm_in_hi, const __grid_cons
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
             if (xx < TV && qy < p.gh && qx < p.gw)
-                part[((size_t)b * p.nchunk + chunk) * p.NQ + qy * p.gw + qx] =
-                    Candidate{v1, i1 == 0x7fffffff ? -1 : i1, v2, i2 == 0x7fffffff ? -1 : i2};
+                part[((size_t)b * p.nchunk + chunk) * p.NQ + qy * p.gw + qx] = cand_pack(cv, ci);
         }
     }
 

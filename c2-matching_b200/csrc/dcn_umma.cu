@@ -8,19 +8,24 @@
 // with fp32 TMEM accumulation, i.e. fp32-grade.
 //
 // Structure = conv3x3_umma.cu with the TMA activation producer replaced by GATHER warps:
-//   K is ordered (deformable group g, tap, channel-in-group); a K chunk = 4 channel octets.
-//   8 gather warps build, per (pixel tile, chunk), the column tile [4 octets][128 px][8] directly in
-//   the tcgen05 K-major no-swizzle layout (hi and lo halves): per (pixel, g, tap) the sampling point
-//   is computed once (raw conv_offset_mask output + pre-offset rebuilt from the index map or read
-//   from the pre_offset tensor, sigmoid mask, validity of the 4 corners), the 8 channels of an octet
-//   are fetched as 16 B (hi) + 16 B (lo) per corner from the octet-planar PSA input, blended in fp32,
-//   multiplied by the mask, split and stored with one 16 B st.shared per half;
+//   K is ordered (deformable group g, tap, channel-in-group); a stage = (128-pixel tile, 4 K octets).
+//   16 gather warps build the column tile [4 octets][128 px][8] directly in the tcgen05 K-major
+//   no-swizzle layout (hi and lo halves).  A gather thread owns (pixel, run of L K-octets that share one
+//   (g, tap) pair), L = min(C/dg/8, 4): the sampling point — raw conv_offset_mask output + pre-offset, sigmoid
+//   mask, the 4 corner offsets and mask-folded bilinear weights — is computed ONCE per (pixel, g, tap) and reused
+//   for the run's octets; for L > 1 the 4 thread groups work on L consecutive stages concurrently.  Per octet:
+//   16 B (hi) + 16 B (lo) per corner from the octet-planar PSA input (L2 evict-last: the input map is re-read by all
+//   nine taps and must stay resident, while offsets / outputs stream through with evict-first), blended (hi halves
+//   in fp32, lo halves in packed fp16), split and stored with one 16 B st.shared per half;
 //   fence.proxy.async + mbarrier hand the stage to the MMA-issuing thread.
-//   Weights stream as 8 KB chunks (bulk copy, 4-deep ring), shared by a group of up to 8 pixel
+//   Pre-offsets: per tile group the index-map cells a tile can touch ((16/s + 2) x (8/s + 2) per tile) are
+//   decoded once into a shared-memory flow table, so the per-(pixel, tap) pre-offset is one ld.shared instead
+//   of an 8-byte global load, two integer divisions and a modulo per (pixel, g, tap).
+//   Weights stream as 8 KB chunks (bulk copy ring), shared by a group of up to 8 pixel
 //   tiles (512/N TMEM accumulators, rotated across groups); every CTA owns an evenly sized contiguous
 //   range of the flat (slice, image, tile) list, so small problems (BASELINE config 4: 200 tiles)
 //   spread over all SMs.  The epilogue (bias, LeakyReLU, PSA and / or fp32 store) is shared with
-//   the plain convolution.  -DC2M_DCN_TRACE prints a %globaltimer trace of CTA 0's pipeline.
+//   the plain convolution.
 // The im2col matrix never exists outside shared memory.
 #include <cstdlib>
 
@@ -34,14 +39,10 @@ constexpr int KOCT = 4;
 constexpr int A_OCT_B = 128 * 16;          // 2048 B: one octet of all 128 pixels (LBO of A)
 constexpr int A_HALF = KOCT * A_OCT_B;     // 8192 B
 constexpr int A_STAGE = 2 * A_HALF;        // 16384 B
-constexpr int NSTAGE = 4;
-constexpr int NBST = 4;
+constexpr int MAX_NSTAGE = 8;
+constexpr int MAX_NBST = 4;
 constexpr int MAXT = 8;
-#ifndef C2M_DCN_NU
-#define C2M_DCN_NU 1
-#endif
-constexpr int NU = C2M_DCN_NU;                       // K octets per gather thread and stage
-constexpr int NGATHER_WARPS = 4 * KOCT / NU;         // thread = (pixel of the tile, NU octets of the chunk)
+constexpr int NGATHER_WARPS = 16;
 constexpr int NTHREADS = 256 + 32 * NGATHER_WARPS;
 constexpr int W_HDR = 256;
 
@@ -57,7 +58,11 @@ struct DcnTc {
     int gh, gw, ref_gw, pre_scale;
     int C, dg, cpg, opp;       // opp = octets per (g, tap) pair = cpg / 8
     int n_ko;                  // real K octets = C/8 * 9
-    int opp_shift;             // log2(opp): octets per (g,tap) pair is 1, 2 or 4 for C/dg in {8,16,32}; -1 otherwise
+    int L, lshift;             // K octets per gather thread and stage (1, 2 or 4), log2
+    int opp_shift;             // log2(opp) when opp is a power of two, else -1 (then L == 1)
+    int nstage, nbst;          // ring depths (activation stages, weight chunks)
+    int sc_shift;              // log2(pre_scale) when the flow table is used (idx given, scale in {1,2,4,8}), else -1
+    int tab_h, tab_w;          // flow-table cells per tile: 16/s + 2, 8/s + 2
     float inv_ref_gw, inv_scale;   // reciprocals for the exact float-assisted integer divisions
 };
 }  // namespace
@@ -71,13 +76,35 @@ __device__ __forceinline__ int fast_div(int n, int d, float inv_d) {
     return q;
 }
 
-#ifdef C2M_DCN_TRACE
-__device__ unsigned long long g_tr[32][4], g_tm[32][3], g_t0[2];
-__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-#define TR(x) x
-#else
-#define TR(x)
-#endif
+// ---- cache-policy helpers: the gathered input map is re-read by all nine taps (keep it in L2), the offset /
+// mask stream and the outputs are touched once (do not let them evict it)
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint4 ldg_keep_v4(const void *ptr, uint64_t pol) {
+    uint4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.b32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(ptr), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ float2 ldg_stream_f2(const float *ptr, uint64_t pol) {
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(ptr), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ float ldg_stream_f1(const float *ptr, uint64_t pol) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(ptr), "l"(pol));
+    return v;
+}
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
@@ -85,16 +112,17 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t w_half = (uint32_t)KOCT * p.N * 16;
     const uint32_t w_chunk = 2 * w_half;
-    uint8_t *sW = smem;                                   // [NBST][hi | lo]
-    uint8_t *sA = smem + NBST * w_chunk;                  // N multiple of 16 -> multiple of 128
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sA + NSTAGE * A_STAGE);
-    uint64_t *full = bars, *empty = full + NSTAGE, *bfull = empty + NSTAGE, *bempty = bfull + NBST,
-             *tfull = bempty + NBST, *tempty = tfull + MAXT;
+    uint8_t *sW = smem;                                   // [nbst][hi | lo]
+    uint8_t *sA = smem + d.nbst * w_chunk;                // N multiple of 16 -> multiple of 128
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sA + d.nstage * A_STAGE);
+    uint64_t *full = bars, *empty = full + MAX_NSTAGE, *bfull = empty + MAX_NSTAGE, *bempty = bfull + MAX_NBST,
+             *tfull = bempty + MAX_NBST, *tempty = tfull + MAXT;
     uint32_t *tmem_base_p = reinterpret_cast<uint32_t *>(tempty + MAXT);
-    float *sbias = reinterpret_cast<float *>(tmem_base_p + 2);
+    float *sbias = reinterpret_cast<float *>(tmem_base_p + 4);                    // [N <= 256], 16 B aligned
+    int4 *tile_info = reinterpret_cast<int4 *>(sbias + 256);                      // [2][MAXT] (b, y0, x0, image pixel base)
+    float2 *flow_tab = reinterpret_cast<float2 *>(tile_info + 2 * MAXT);          // [2][T][tab_h * tab_w]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    TR(if (blockIdx.x == 0 && threadIdx.x == 0) g_t0[0] = gtime();)
     const int tiles_img = p.tiles_x * p.tiles_y;
     // Work = flat list of (Cout slice, image, pixel tile); every CTA owns one contiguous, evenly sized range
     // of it and walks the range in groups of <= T tiles that share the streamed weight chunks.
@@ -106,10 +134,11 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
     const uint32_t need_cols = (uint32_t)p.N * p.T;
     const uint32_t tmem_cols = need_cols <= 32 ? 32 : need_cols <= 64 ? 64 : need_cols <= 128 ? 128
                                : need_cols <= 256 ? 256 : 512;
+    const int nstage_mask = d.nstage - 1;                // ring depths are powers of two
 
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < NSTAGE; ++i) { mbar_init(&full[i], NGATHER_WARPS); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < NBST; ++i) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], 1); }
+        for (int i = 0; i < d.nstage; ++i) { mbar_init(&full[i], NGATHER_WARPS >> d.lshift); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < d.nbst; ++i) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], 1); }
         for (int i = 0; i < MAXT; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
         fence_mbar_init();
     }
@@ -121,8 +150,6 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_p;
-    TR(if (blockIdx.x == 0 && threadIdx.x == 0) g_t0[1] = gtime();)
-    TR(int trs = 0;)
     const int sw = *reinterpret_cast<const int *>(q.wblob);
 
     auto group = [&](int pos, int &slice, int &nt) {
@@ -150,7 +177,7 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
                         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                         ::"r"(smem_u32(sW + bst * w_chunk)), "l"(src), "r"(w_chunk), "r"(smem_u32(&bfull[bst]))
                         : "memory");
-                    if (++bst == NBST) { bst = 0; bphase ^= 1; }
+                    if (++bst == d.nbst) { bst = 0; bphase ^= 1; }
                 }
             }
         }
@@ -168,7 +195,6 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
                 for (int kc = 0; kc < p.nkc; ++kc) {
                     mbar_wait(&bfull[bst], bphase);
                     tc_fence_after();
-                    TR(if (blockIdx.x == 0 && trs < 32) g_tm[trs][0] = gtime();)
                     const uint32_t w_hi = smem_u32(sW + bst * w_chunk), w_lo = w_hi + w_half;
                     for (int t = 0; t < nt; ++t) {
                         int a = abase + t;
@@ -180,7 +206,6 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
                         const uint32_t dacc = tmem_base + a * p.N;
                         mbar_wait(&full[stage], phase);
                         tc_fence_after();
-                        TR(if (blockIdx.x == 0 && trs < 32) g_tm[trs][1] = gtime();)
                         const uint32_t a_hi = smem_u32(sA + stage * A_STAGE), a_lo = a_hi + A_HALF;
 #pragma unroll
                         for (int j = 0; j < KOCT / 2; ++j) {
@@ -194,12 +219,11 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
                             umma_f16(dacc, dal, dbh, idesc, 1);
                         }
                         umma_commit(&empty[stage]);
-                        TR(if (blockIdx.x == 0 && trs < 32) { g_tm[trs][2] = gtime(); ++trs; })
-                        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                        if (++stage == d.nstage) { stage = 0; phase ^= 1; }
                         if (kc == p.nkc - 1) { umma_commit(&tfull[a]); tph ^= 1u << a; }
                     }
                     umma_commit(&bempty[bst]);
-                    if (++bst == NBST) { bst = 0; bphase ^= 1; }
+                    if (++bst == d.nbst) { bst = 0; bphase ^= 1; }
                 }
                 abase += nt;
                 if (abase >= nacc) abase -= nacc;
@@ -248,202 +272,204 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
         }
     } else {
         // ================================ gather producers ==================================
-        // Thread = (pixel m of the tile, octet pair oh of the chunk).  Per stage two dependent
-        // memory round trips exist (offsets/mask/idx -> corner addresses -> corner values); the
-        // first one is taken off the critical path by fetching the NEXT stage's metadata while the
-        // current stage's corners are in flight.
+        // 4 thread groups of 128 (thread = pixel m of the tile).  With L K-octets per thread a stage has NS = 4 / L
+        // thread slots, so the 4 groups split into NG = L stage groups that work on consecutive stages concurrently:
+        // group grp -> (stage residue sg = grp / NS, slot = grp % NS); slot covers octets [slot*L, slot*L + L).
         const int g_tid = threadIdx.x - 256;
         const int m = g_tid & 127;
-        const int oh = g_tid >> 7;
+        const int grp = g_tid >> 7;
+        const int L = d.L, NG = L, NS = KOCT >> d.lshift;
+        const int sg = grp / NS, slot = grp - sg * NS;
         const int P = p.H * p.W;
-        struct Meta { float off_h, off_w, mr; int v; };
-        int stage = 0, phase = 0;
-        const float inv_ti = 1.f / (float)tiles_img;
-        const size_t x_img = (size_t)d.C8 * P * 8, om_img = (size_t)(d.mask ? 2 : 3) * d.dg * 9 * P;
-        for (int pos = w_begin, nt = 0; pos < w_end; pos += nt) {
+        const int mrow = m / T_C, mcol = m % T_C;
+        const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
+        const size_t x_img = (size_t)d.C8 * P * 8;
+        const int om_mask_base = 2 * d.dg * 9;
+        const int tab_n = d.tab_h * d.tab_w;
+        // cell of this thread's pixel inside a tile's flow table, before the tap shift (+2 halo cells)
+        const int cell0 = d.sc_shift >= 0 ? ((mrow >> d.sc_shift) + 2) * d.tab_w + (mcol >> d.sc_shift) + 2 : 0;
+        struct Meta { float off_h, off_w, mr; };
+        int ring = 0;                                       // stages issued by this CTA so far (all groups agree)
+        int gi = 0;                                         // tile-group counter (table double buffer)
+        for (int pos = w_begin, nt = 0; pos < w_end; pos += nt, ++gi) {
             int slice;
             group(pos, slice, nt);
             const int r0g = pos - slice * TT;               // (image, tile) index of the group's first tile
             const int n_steps = p.nkc * nt;
+            int4 *tinfo = tile_info + (gi & 1) * MAXT;
+            float2 *tab = flow_tab + (size_t)(gi & 1) * p.T * tab_n;
 
-            // (kc, t) and the pixel of this thread in tile t are advanced incrementally; all divisions by
-            // run-time values go through fast_div / shifts
-            const int mrow = m / T_C, mcol = m % T_C;
-            const float inv_tx = 1.f / (float)p.tiles_x;
-            const int opp_shift = d.opp_shift;
-            const int om_mask_base = 2 * d.dg * 9;
+            // ---- per tile group: tile origins and the decoded flow of every index-map cell a tile can touch
+            if (g_tid < nt) {
+                const int r = r0g + g_tid;
+                const int b = r / tiles_img, tt = r - b * tiles_img;
+                const int ty = tt / p.tiles_x;
+                tinfo[g_tid] = make_int4(b, ty * T_R, (tt - ty * p.tiles_x) * T_C, 0);
+            }
+            if (d.sc_shift >= 0) {
+                for (int i = g_tid; i < nt * tab_n; i += 32 * NGATHER_WARPS) {
+                    const int t = i / tab_n, c = i - t * tab_n;
+                    const int r = r0g + t;
+                    const int b = r / tiles_img, tt = r - b * tiles_img;
+                    const int ty = tt / p.tiles_x, tx = tt - ty * p.tiles_x;
+                    const int cy = c / d.tab_w, cx = c - cy * d.tab_w;
+                    const int acy = ((ty * T_R) >> d.sc_shift) - 2 + cy, acx = ((tx * T_C) >> d.sc_shift) - 2 + cx;
+                    float2 fl = make_float2(0.f, 0.f);
+                    if (acy >= 0 && acx >= 0 && acy < d.gh && acx < d.gw) {
+                        const int v = (int)d.idx[((long long)b * d.gh + acy) * d.gw + acx];
+                        const int vy = fast_div(v, d.ref_gw, d.inv_ref_gw), vx = v - vy * d.ref_gw;
+                        fl = make_float2((float)((vx - acx) << d.sc_shift), (float)((vy - acy) << d.sc_shift));   // (x, y)
+                    }
+                    tab[i] = fl;
+                }
+            }
+            asm volatile("bar.sync 2, 512;" ::: "memory");
 
-            // metadata fetch for (kc, t, u): raw offsets + mask logit + index-map entry
-            auto fetch = [&](int kc, int t, bool in_range, int u, Meta &mt, int &pair_out, bool &live) {
-                const int b = fast_div(r0g + t, tiles_img, inv_ti);
-                const int tt = r0g + t - b * tiles_img;
-                const float *omb = d.om + b * om_img;
-                const int ty = fast_div(tt, p.tiles_x, inv_tx);
-                const int y = ty * T_R + mrow, xx = (tt - ty * p.tiles_x) * T_C + mcol;
-                const int ko = kc * KOCT + oh * NU + u;
-                live = in_range && y < p.H && xx < p.W && ko < d.n_ko;
-                pair_out = opp_shift >= 0 ? (ko >> opp_shift) : ko / d.opp;
+            // ---- metadata of unit (kc, t): raw offsets (+ pre-offset) and mask logit of this thread's pixel
+            auto fetch = [&](int kc, int t, bool in_range, Meta &mt, int &pair_out, int &y_out, int &x_out, int &b_out,
+                             bool &live) {
                 mt.off_h = mt.off_w = mt.mr = 0.f;
-                mt.v = -1;
+                pair_out = 0; y_out = x_out = b_out = 0;
+                live = false;
+                if (!in_range) return;
+                const int4 ti = tinfo[t];
+                const int b = ti.x, y = ti.y + mrow, xx = ti.z + mcol;
+                const int ko = kc * KOCT + slot * L;
+                live = y < p.H && xx < p.W && ko < d.n_ko;
+                pair_out = d.opp_shift >= 0 ? (ko >> d.opp_shift) : ko / d.opp;
+                y_out = y; x_out = xx; b_out = b;
                 if (!live) return;
                 const int g = pair_out / 9, tap = pair_out - g * 9;
-                const int jj = g * 9 + tap, pp = y * p.W + xx;
+                const int jj = pair_out, pp = y * p.W + xx;
                 if (d.om_c8 > 0) {     // 2jj is even: the (y, x) offset pair shares an octet
                     const float *ob = d.om + (size_t)b * d.om_c8 * P * 8;
                     const int c0 = 2 * jj, cm = om_mask_base + jj;
-                    const float2 of = *reinterpret_cast<const float2 *>(ob + ((c0 >> 3) * P + pp) * 8 + (c0 & 7));
+                    const float2 of = ldg_stream_f2(ob + ((size_t)(c0 >> 3) * P + pp) * 8 + (c0 & 7), pol_stream);
                     mt.off_h = of.x;
                     mt.off_w = of.y;
-                    mt.mr = ob[((cm >> 3) * P + pp) * 8 + (cm & 7)];
+                    mt.mr = ldg_stream_f1(ob + ((size_t)(cm >> 3) * P + pp) * 8 + (cm & 7), pol_stream);
                 } else {
-                    mt.off_h = omb[(2 * jj) * P + pp];
-                    mt.off_w = omb[(2 * jj + 1) * P + pp];
-                    mt.mr = d.mask ? d.mask[((size_t)b * d.dg * 9 + jj) * P + pp] : omb[(om_mask_base + jj) * P + pp];
+                    const float *omb = d.om + (size_t)b * (d.mask ? 2 : 3) * d.dg * 9 * P;
+                    mt.off_h = ldg_stream_f1(omb + (size_t)(2 * jj) * P + pp, pol_stream);
+                    mt.off_w = ldg_stream_f1(omb + (size_t)(2 * jj + 1) * P + pp, pol_stream);
+                    mt.mr = d.mask ? ldg_stream_f1(d.mask + ((size_t)b * d.dg * 9 + jj) * P + pp, pol_stream)
+                                   : ldg_stream_f1(omb + (size_t)(om_mask_base + jj) * P + pp, pol_stream);
                 }
+                const int ki = tap / 3, kj = tap - ki * 3;
                 if (d.pre) {
                     const float2 pq = *reinterpret_cast<const float2 *>(d.pre + (((size_t)b * 9 + tap) * P + pp) * 2);
                     mt.off_w += pq.x;
                     mt.off_h += pq.y;
-                } else if (d.idx) {
-                    const long long *idxb = d.idx + (long long)b * d.gh * d.gw;
-                    const int sc = d.pre_scale, ki = tap / 3, kj = tap - ki * 3;
+                } else if (d.sc_shift >= 0) {
+                    const float2 fl = tab[t * tab_n + cell0 - ki * d.tab_w - kj];
+                    mt.off_w += fl.x;
+                    mt.off_h += fl.y;
+                } else if (d.idx) {                       // scales the table does not cover: decode in place
+                    const int sc = d.pre_scale;
                     const int ys = y - sc * ki, xs = xx - sc * kj;
                     if (ys >= 0 && xs >= 0) {
                         const int yy = fast_div(ys, sc, d.inv_scale), xg = fast_div(xs, sc, d.inv_scale);
-                        if (yy < d.gh && xg < d.gw) mt.v = (int)idxb[yy * d.gw + xg];
+                        if (yy < d.gh && xg < d.gw) {
+                            const int v = (int)d.idx[((long long)b * d.gh + yy) * d.gw + xg];
+                            const int vy = fast_div(v, d.ref_gw, d.inv_ref_gw), vx = v - vy * d.ref_gw;
+                            mt.off_w += (float)(sc * (vx - xg));
+                            mt.off_h += (float)(sc * (vy - yy));
+                        }
                     }
                 }
             };
 
-            Meta mt[NU], nx[NU];
-            int pr[NU], npr[NU];
-            bool lv[NU], nlv[NU];
-#pragma unroll
-            for (int u = 0; u < NU; ++u) fetch(0, 0, n_steps > 0, u, mt[u], pr[u], lv[u]);
-            int kc = 0, t = 0;
-            for (int step = 0; step < n_steps; ++step) {
-                const int b = fast_div(r0g + t, tiles_img, inv_ti);
-                const int tt = r0g + t - b * tiles_img;
-                const __half *xh = d.x_hi + b * x_img;
-                const __half *xl = d.x_lo + b * x_img;
-                TR(const bool trc = blockIdx.x == 0 && threadIdx.x == 256 && trs < 32; if (trc) g_tr[trs][0] = gtime();)
-                const int ty = fast_div(tt, p.tiles_x, inv_tx);
-                const int y = ty * T_R + mrow, xx = (tt - ty * p.tiles_x) * T_C + mcol;
-                // next (kc, t)
-                int nkc_ = kc, nt_ = t + 1;
-                if (nt_ == nt) { nt_ = 0; ++nkc_; }
-                // ---- sampling points of the two octets
-                int o[NU][4];
-                float wq[NU][4], mk[NU];
-#pragma unroll
-                for (int u = 0; u < NU; ++u) {
-                    o[u][0] = o[u][1] = o[u][2] = o[u][3] = 0;
-                    wq[u][0] = wq[u][1] = wq[u][2] = wq[u][3] = 0.f;
-                    mk[u] = 0.f;
-                    if (lv[u]) {
-                        const int g = pr[u] / 9, tap = pr[u] - g * 9, ki = tap / 3, kj = tap - ki * 3;
-                        float off_h = mt[u].off_h, off_w = mt[u].off_w;
-                        if (mt[u].v >= 0) {
-                            const int sc = d.pre_scale;
-                            const int yy = fast_div(y - sc * ki, sc, d.inv_scale), xg = fast_div(xx - sc * kj, sc, d.inv_scale);
-                            const int vy = fast_div(mt[u].v, d.ref_gw, d.inv_ref_gw), vx = mt[u].v - vy * d.ref_gw;
-                            off_w += (float)(sc * (vx - xg));
-                            off_h += (float)(sc * (vy - yy));
-                        }
-                        const float h_im = (float)(y - 1 + ki) + off_h;
-                        const float w_im = (float)(xx - 1 + kj) + off_w;
-                        if (h_im > -1.f && w_im > -1.f && h_im < (float)p.H && w_im < (float)p.W) {
-                            const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
-                            const int h_high = h_low + 1, w_high = w_low + 1;
-                            const float lh = h_im - h_low, lw = w_im - w_low;
-                            const float hh = 1.f - lh, hw = 1.f - lw;
-                            const bool tv = h_low >= 0, bv = h_high <= p.H - 1, lvv = w_low >= 0, rv = w_high <= p.W - 1;
-                            // channel octet of this K octet, as an element offset of its [H][W][8] plane
-                            const int ko = kc * KOCT + oh * NU + u;
-                            const int oct_c = g * (d.cpg / 8) + (ko - (opp_shift >= 0 ? (pr[u] << opp_shift) : pr[u] * d.opp));
-                            const int cbase = oct_c * P * 8;
-                            const int r0 = (h_low * p.W + w_low) * 8 + cbase;
-                            if (tv && lvv) { o[u][0] = r0; wq[u][0] = hh * hw; }
-                            if (tv && rv) { o[u][1] = r0 + 8; wq[u][1] = hh * lw; }
-                            if (bv && lvv) { o[u][2] = r0 + p.W * 8; wq[u][2] = lh * hw; }
-                            if (bv && rv) { o[u][3] = r0 + p.W * 8 + 8; wq[u][3] = lh * lw; }
-                            // sigmoid to ~2 ulp: the TC path is fp32-grade, not bit-exact
-                            mk[u] = d.mask ? mt[u].mr : __fdividef(1.f, 1.f + __expf(-mt[u].mr));
-                        }
+            // my units of this group: steps sg, sg + NG, ...; (kc, t) advanced incrementally
+            int kc = 0, t = sg;
+            while (t >= nt) { t -= nt; ++kc; }
+            Meta mt, nx;
+            int pr, npr, y, ny, xx, nxx, b, nb;
+            bool lv, nlv;
+            fetch(kc, t, sg < n_steps, mt, pr, y, xx, b, lv);
+            for (int step = sg; step < n_steps; step += NG) {
+                int nkc_ = kc, nt_ = t + NG;
+                while (nt_ >= nt) { nt_ -= nt; ++nkc_; }
+                // ---- sampling point of the unit's (pixel, g, tap): dcn_v2_im2col_cuda.cu:25-54,172-190
+                int o0 = 0, o1 = 0, o2 = 0, o3 = 0;
+                float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
+                int oct_c = 0;
+                if (lv) {
+                    const int g = pr / 9, tap = pr - g * 9, ki = tap / 3, kj = tap - ki * 3;
+                    const float h_im = (float)(y - 1 + ki) + mt.off_h;
+                    const float w_im = (float)(xx - 1 + kj) + mt.off_w;
+                    if (h_im > -1.f && w_im > -1.f && h_im < (float)p.H && w_im < (float)p.W) {
+                        const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
+                        const int h_high = h_low + 1, w_high = w_low + 1;
+                        const float lh = h_im - h_low, lw = w_im - w_low;
+                        const float hh = 1.f - lh, hw = 1.f - lw;
+                        const bool tv = h_low >= 0, bv = h_high <= p.H - 1, lvv = w_low >= 0, rv = w_high <= p.W - 1;
+                        // sigmoid to ~2 ulp: the TC path is fp32-grade, not bit-exact; the mask is folded into the weights
+                        const float mk = d.mask ? mt.mr : __fdividef(1.f, 1.f + __expf(-mt.mr));
+                        const int r0 = (h_low * p.W + w_low) * 8;
+                        if (tv && lvv) { o0 = r0; w0 = hh * hw * mk; }
+                        if (tv && rv) { o1 = r0 + 8; w1 = hh * lw * mk; }
+                        if (bv && lvv) { o2 = r0 + p.W * 8; w2 = lh * hw * mk; }
+                        if (bv && rv) { o3 = r0 + p.W * 8 + 8; w3 = lh * lw * mk; }
                     }
+                    // first channel octet of this run: group g, octets [ko - pair * opp, +L) of the group
+                    const int ko = kc * KOCT + slot * L;
+                    oct_c = g * d.opp + (ko - (d.opp_shift >= 0 ? (pr << d.opp_shift) : pr * d.opp));
                 }
-                // octet-planar operand: the 32 lanes of a warp (4 rows x 8 pixels) read 16 B each from runs of
-                // adjacent pixels (8 lines per request instead of 32 with a channels-last fp32 input)
-                uint4 ch[NU][4], cl[NU][4];
-#pragma unroll
-                for (int u = 0; u < NU; ++u)
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        ch[u][c] = *reinterpret_cast<const uint4 *>(xh + o[u][c]);
-                        cl[u][c] = *reinterpret_cast<const uint4 *>(xl + o[u][c]);
-                    }
-#pragma unroll
-                for (int u = 0; u < NU; ++u) fetch(nkc_, nt_, step + 1 < n_steps, u, nx[u], npr[u], nlv[u]);
-                // ---- blend, modulate, split.  value = hi + lo: the hi halves are blended in fp32, the lo halves
-                // (|lo| <= 2^-11 |value|) in packed fp16 — their rounding lands at 2^-22 of the value; the
-                // sigmoid mask is folded into the four corner weights
-                uint4 h_out[NU], l_out[NU];
-#pragma unroll
-                for (int u = 0; u < NU; ++u) {
-                    float wm[4];
-                    __half2 wh[4];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        wm[c] = wq[u][c] * mk[u];
-                        wh[c] = __float2half2_rn(wm[c]);
-                    }
-                    const __half2 *hp[4], *lp[4];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        hp[c] = reinterpret_cast<const __half2 *>(&ch[u][c]);
-                        lp[c] = reinterpret_cast<const __half2 *>(&cl[u][c]);
-                    }
+                const __half *xh = d.x_hi + b * x_img + (size_t)oct_c * P * 8;
+                const __half *xl = d.x_lo + b * x_img + (size_t)oct_c * P * 8;
+                const __half2 wh0 = __float2half2_rn(w0), wh1 = __float2half2_rn(w1), wh2 = __float2half2_rn(w2),
+                              wh3 = __float2half2_rn(w3);
+                const int stage_idx = ring + step;
+                const int rs = stage_idx & nstage_mask;
+                const uint32_t rphase = (uint32_t)(stage_idx >> (31 - __clz(d.nstage))) & 1u;
+                uint8_t *sdst = sA + rs * A_STAGE + (slot * L) * A_OCT_B + m * 16;
+                // next unit's metadata goes out before this unit's corner fetches come back
+                fetch(nkc_, nt_, step + NG < n_steps, nx, npr, ny, nxx, nb, nlv);
+#pragma unroll 1
+                for (int u = 0; u < L; ++u) {
+                    // octet-planar operand: the 32 lanes of a warp (4 rows x 8 pixels) read 16 B each from runs of
+                    // adjacent pixels (8 lines per request instead of 32 with a channels-last fp32 input)
+                    const size_t po = (size_t)u * P * 8;
+                    const uint4 ch0 = ldg_keep_v4(xh + po + o0, pol_keep), ch1 = ldg_keep_v4(xh + po + o1, pol_keep);
+                    const uint4 ch2 = ldg_keep_v4(xh + po + o2, pol_keep), ch3 = ldg_keep_v4(xh + po + o3, pol_keep);
+                    const uint4 cl0 = ldg_keep_v4(xl + po + o0, pol_keep), cl1 = ldg_keep_v4(xl + po + o1, pol_keep);
+                    const uint4 cl2 = ldg_keep_v4(xl + po + o2, pol_keep), cl3 = ldg_keep_v4(xl + po + o3, pol_keep);
+                    // ---- blend, modulate, split.  value = hi + lo: the hi halves are blended in fp32, the lo halves
+                    // (|lo| <= 2^-11 |value|) in packed fp16 — their rounding lands at 2^-22 of the value
+                    const __half2 *hp0 = reinterpret_cast<const __half2 *>(&ch0), *hp1 = reinterpret_cast<const __half2 *>(&ch1);
+                    const __half2 *hp2 = reinterpret_cast<const __half2 *>(&ch2), *hp3 = reinterpret_cast<const __half2 *>(&ch3);
+                    const __half2 *lp0 = reinterpret_cast<const __half2 *>(&cl0), *lp1 = reinterpret_cast<const __half2 *>(&cl1);
+                    const __half2 *lp2 = reinterpret_cast<const __half2 *>(&cl2), *lp3 = reinterpret_cast<const __half2 *>(&cl3);
                     __align__(16) __half2 h4[4];
                     __align__(16) __half2 l4[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        __half2 ls = __hmul2(wh[0], lp[0][j]);
-                        ls = __hfma2(wh[1], lp[1][j], ls);
-                        ls = __hfma2(wh[2], lp[2][j], ls);
-                        ls = __hfma2(wh[3], lp[3][j], ls);
+                        __half2 ls = __hmul2(wh0, lp0[j]);
+                        ls = __hfma2(wh1, lp1[j], ls);
+                        ls = __hfma2(wh2, lp2[j], ls);
+                        ls = __hfma2(wh3, lp3[j], ls);
                         const float2 lf = __half22float2(ls);
-                        const float2 a = __half22float2(hp[0][j]), bq = __half22float2(hp[1][j]);
-                        const float2 cq = __half22float2(hp[2][j]), dq = __half22float2(hp[3][j]);
-                        const float vx = fmaf(wm[0], a.x, fmaf(wm[1], bq.x, fmaf(wm[2], cq.x, fmaf(wm[3], dq.x, lf.x))));
-                        const float vy = fmaf(wm[0], a.y, fmaf(wm[1], bq.y, fmaf(wm[2], cq.y, fmaf(wm[3], dq.y, lf.y))));
+                        const float2 a = __half22float2(hp0[j]), bq = __half22float2(hp1[j]);
+                        const float2 cq = __half22float2(hp2[j]), dq = __half22float2(hp3[j]);
+                        const float vx = fmaf(w0, a.x, fmaf(w1, bq.x, fmaf(w2, cq.x, fmaf(w3, dq.x, lf.x))));
+                        const float vy = fmaf(w0, a.y, fmaf(w1, bq.y, fmaf(w2, cq.y, fmaf(w3, dq.y, lf.y))));
                         const __half2 hq = __floats2half2_rn(vx, vy);
                         const float2 hf = __half22float2(hq);
                         h4[j] = hq;
                         l4[j] = __floats2half2_rn(vx - hf.x, vy - hf.y);
                     }
-                    h_out[u] = *reinterpret_cast<const uint4 *>(h4);
-                    l_out[u] = *reinterpret_cast<const uint4 *>(l4);
-                }
-                TR(if (trc) g_tr[trs][1] = gtime();)
-                mbar_wait(&empty[stage], phase ^ 1);
-                TR(if (trc) g_tr[trs][2] = gtime();)
-                uint8_t *sdst = sA + stage * A_STAGE;
-#pragma unroll
-                for (int u = 0; u < NU; ++u) {
-                    const int oct = oh * NU + u;
-                    *reinterpret_cast<uint4 *>(sdst + oct * A_OCT_B + m * 16) = h_out[u];
-                    *reinterpret_cast<uint4 *>(sdst + A_HALF + oct * A_OCT_B + m * 16) = l_out[u];
+                    if (u == 0) mbar_wait(&empty[rs], rphase ^ 1u);
+                    *reinterpret_cast<uint4 *>(sdst + u * A_OCT_B) = *reinterpret_cast<const uint4 *>(h4);
+                    *reinterpret_cast<uint4 *>(sdst + A_HALF + u * A_OCT_B) = *reinterpret_cast<const uint4 *>(l4);
                 }
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&full[stage]);
-                TR(if (trc) { g_tr[trs][3] = gtime(); } ++trs;)
-                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-#pragma unroll
-                for (int u = 0; u < NU; ++u) { mt[u] = nx[u]; pr[u] = npr[u]; lv[u] = nlv[u]; }
+                if (lane == 0) mbar_arrive(&full[rs]);
+                mt = nx; pr = npr; lv = nlv; y = ny; xx = nxx; b = nb;
                 kc = nkc_;
                 t = nt_;
             }
+            ring += n_steps;
         }
     }
 
@@ -453,13 +479,6 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
         tc_fence_after();
         tmem_dealloc(tmem_base, tmem_cols);
     }
-    TR(if (blockIdx.x == 0 && threadIdx.x == 0) {
-        const unsigned long long z = g_t0[0];
-        printf("TRACE setup %llu end %llu\n", g_t0[1] - z, gtime() - z);
-        for (int i = 0; i < 24; ++i)
-            printf("  s%02d gather top %6llu loads %6llu wait %6llu arr %6llu | mma bfull %6llu full %6llu commit %6llu\n", i,
-                   g_tr[i][0] - z, g_tr[i][1] - z, g_tr[i][2] - z, g_tr[i][3] - z, g_tm[i][0] - z, g_tm[i][1] - z, g_tm[i][2] - z);
-    })
 }
 
 // blob: header | [slice][kc][hi|lo][octet 4][N][8], K ordered (g, tap, channel-in-group)
@@ -581,13 +600,35 @@ extern "C" int c2m_dcn_v2_fused_tc(const c2m_dcn_tc_args *a, c2m_stream_t stream
     d.om = a->om; d.pre = a->pre; d.idx = reinterpret_cast<const long long *>(a->idx);
     d.gh = a->gh; d.gw = a->gw; d.ref_gw = a->ref_gw; d.pre_scale = a->pre_scale;
     d.C = a->C; d.dg = a->dg; d.cpg = a->C / a->dg; d.opp = d.cpg / 8; d.n_ko = (a->C / 8) * 9;
-    d.opp_shift = d.opp == 1 ? 0 : d.opp == 2 ? 1 : d.opp == 4 ? 2 : d.opp == 8 ? 3 : -1;
+    d.opp_shift = -1;
+    for (int sft = 0; sft < 8; ++sft)
+        if (d.opp == (1 << sft)) d.opp_shift = sft;
+    // K octets per gather thread: the (g, tap) run inside a 4-octet stage when C/dg/8 is a power of two
+    d.L = d.opp_shift < 0 ? 1 : (d.opp >= KOCT ? KOCT : d.opp);
+    d.lshift = d.L == 4 ? 2 : d.L == 2 ? 1 : 0;
     d.inv_ref_gw = a->ref_gw > 0 ? 1.f / (float)a->ref_gw : 0.f;
     d.inv_scale = a->pre_scale > 0 ? 1.f / (float)a->pre_scale : 1.f;
+    // flow table: index-map cells a 16x8 tile (+ the 2-cell tap shift) can touch, when the scale divides the tile
+    d.sc_shift = -1;
+    d.tab_h = d.tab_w = 0;
+    if (!a->pre && a->idx)
+        for (int sft = 0; sft < 4; ++sft)
+            if (a->pre_scale == (1 << sft)) {
+                d.sc_shift = sft;
+                d.tab_h = (T_R >> sft) + 2;
+                d.tab_w = (T_C >> sft) + 2;
+            }
     C2M_CHECK_ARG((long long)a->H * a->W * (27 * a->dg + 7) < (1ll << 31) && (long long)a->H * a->W * a->C < (1ll << 31),
                   "dcn_v2_fused_tc: map too large for 32-bit in-kernel indexing");
     C2M_CHECK_ARG(a->idx == nullptr || (long long)a->gh * a->gw < (1 << 23), "dcn_v2_fused_tc: index map too large");
-    const size_t smem = (size_t)NBST * 2 * KOCT * p.N * 16 + NSTAGE * A_STAGE + 4096;
+    // ring depths (powers of two): with L octets per thread, L stage groups fill consecutive stages concurrently
+    const size_t w_chunk = (size_t)2 * KOCT * p.N * 16;
+    d.nstage = d.L == 1 ? 4 : 8;
+    const size_t fixed = (size_t)d.nstage * A_STAGE + (2 * MAX_NSTAGE + 2 * MAX_NBST + 2 * MAXT) * 8 + 16 + 256 * 4 +
+                         2 * MAXT * 16 + (size_t)2 * p.T * d.tab_h * d.tab_w * 8 + 1024 + 128;
+    d.nbst = fixed + 4 * w_chunk <= 227 * 1024 ? 4 : 2;
+    const size_t smem = fixed + d.nbst * w_chunk;
+    C2M_CHECK_ARG(smem <= 227 * 1024, "dcn_v2_fused_tc: %zu bytes of shared memory needed", smem);
     C2M_CUDA(cudaFuncSetAttribute(dcn_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 0;
     C2M_CUDA(cudaGetDevice(&dev));
