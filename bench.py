@@ -335,6 +335,88 @@ def run_ours(args, rank, world, local_rank):
         torch.distributed.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------- config 5 (N1: sharded evaluation)
+def run_config5(args, rank, world, local_rank):
+    """BASELINE config 5: 126 synthetic CUFED5-shape pairs (config-2 shapes) through the model-level driver
+    `RefRestorationModel.validation` — dataset decode + PIL resizes in loader workers, rank::world sharding at the
+    index level, same-shape batches, forward, async D2H, PSNR/SSIM on a thread pool, final metric all-gather.
+    value = pairs of ALL ranks / max-over-ranks wall time (barrier + sync on both sides)."""
+    import __graft_entry__ as entry
+    from c2m_b200.dist import max_over_ranks
+    from mmsr.data import create_dataloader, create_dataset
+    from mmsr.models.ref_restoration_model import RefRestorationModel
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    dist_on = world > 1
+    if dist_on:
+        torch.distributed.init_process_group('nccl', device_id=dev)
+        if local_rank == 0:
+            entry.build()
+        torch.distributed.barrier()
+    entry.build()
+    opt = {'name': 'config5', 'suffix': None, 'scale': 4, 'crop_border': None, 'dist': dist_on, 'is_train': False,
+           'post_workers': args.post_workers,
+           'network_g': {'type': 'RestorationNet', 'ngf': 64, 'n_blocks': 16, 'groups': 8},
+           'network_map': {'type': 'CorrespondenceGenerationArch', 'patch_size': 3, 'stride': 1,
+                           'vgg_layer_list': ['relu1_1', 'relu2_1', 'relu3_1'], 'vgg_type': 'vgg19', 'vgg_pretrained': False},
+           'network_extractor': {'type': 'ContrasExtractorSep'}, 'path': {}}
+    model = RefRestorationModel(opt)
+    for net, sd in zip((model.net_extractor, model.net_map, model.net_g), seeded_weights()):
+        net.load_state_dict(sd, strict=True)
+    dopt = {'name': 'config5_synth', 'type': 'SyntheticRefDataset', 'phase': 'test', 'num': args.pairs, 'gt_size': 4 * LR,
+            'ref_size': REF, 'scale': 4, 'num_workers': args.loader_workers, 'batch_size': args.eval_batch,
+            'prefetch_factor': 2}
+    dset = create_dataset(dopt)
+    # warm-up on a few pairs (weight packing, allocator, loader worker start-up are not part of the metric)
+    wopt = dict(dopt, num=max(2, args.eval_batch) * world)
+    model.validation(create_dataloader(create_dataset(wopt), wopt, dist=dist_on), 0)
+
+    def barrier():
+        if dist_on:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    loader = create_dataloader(dset, dopt, dist=dist_on)
+    barrier()
+    t0 = time.perf_counter()
+    res = model.validation(loader, 0)
+    barrier()
+    wall = max_over_ranks(time.perf_counter() - t0, dev)
+    clocks = sampler.stop() if sampler else None
+    stage = torch.tensor([res['rank_loader_wait_s'], res['rank_submit_s'], res['rank_wall_s'], float(res['rank_images'])],
+                         dtype=torch.float64, device=dev)
+    if dist_on:
+        stages = [torch.zeros_like(stage) for _ in range(world)]
+        torch.distributed.all_gather(stages, stage)
+    else:
+        stages = [stage]
+    if rank == 0:
+        per_rank = [{'images': int(s[3]), 'wall_s': round(float(s[2]), 3), 'loader_wait_s': round(float(s[0]), 3),
+                     'forward_submit_s': round(float(s[1]), 3)} for s in stages]
+        worst = max(per_rank, key=lambda r: r['wall_s'])
+        limiting = ('host loader (GPU waits for decoded pairs)' if worst['loader_wait_s'] > 0.3 * worst['wall_s'] else
+                    'host post-processing / submit' if worst['forward_submit_s'] > 0.8 * worst['wall_s'] else 'GPU forward')
+        physical, logical = host_cores()
+        print(json.dumps({
+            'metric': 'SR images/sec, sharded evaluation of 126 CUFED5-shape pairs (config 5)', 'value': args.pairs / wall,
+            'unit': 'images/s', 'n_gpus': world, 'steps': 1, 'warmup': 1, 'ms_per_step': wall * 1e3, 'higher_is_better': True,
+            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': f'config5: {args.pairs} synthetic pairs (GT 640x640, Ref 500x500 zero-padded), RefRestorationModel.validation: '
+                                   'dataset decode + PIL bicubic in loader workers, rank::world index sharding, same-shape batches, '
+                                   'forward, async D2H, PSNR/PSNR_Y/SSIM_Y on a thread pool, final all-gather of the metric rows',
+                       'eval_batch': args.eval_batch, 'loader_workers_per_rank': args.loader_workers,
+                       'post_workers_per_rank': args.post_workers, 'host_cores': {'physical': physical, 'logical': logical},
+                       'parallelism': f'dp{world} (pair list sharded rank::world; collective = metric all-gather only)'},
+            'validation': {k: res[k] for k in ('psnr', 'psnr_y', 'ssim_y', 'n')}, 'per_rank': per_rank,
+            'limiting_stage': limiting, 'clocks': clocks,
+        }), flush=True)
+    if dist_on:
+        torch.distributed.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -345,12 +427,20 @@ def main():
     ap.add_argument('--channels-last', type=int, default=0)
     ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the CPU oracle leg (cpu_baseline + parity)')
     ap.add_argument('--no-micro', action='store_true', help='skip the config-3 / config-4 microbenchmarks')
+    ap.add_argument('--workload', choices=['config2', 'config5'], default='config2',
+                    help='config2 (default, the headline metric) or config5: sharded evaluation of 126 pairs')
+    ap.add_argument('--pairs', type=int, default=126)
+    ap.add_argument('--eval-batch', type=int, default=4)
+    ap.add_argument('--loader-workers', type=int, default=6)
+    ap.add_argument('--post-workers', type=int, default=6)
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     if args.impl == 'reference':
         run_reference(args, rank)
+    elif args.workload == 'config5':
+        run_config5(args, rank, world, local_rank)
     else:
         run_ours(args, rank, world, local_rank)
 

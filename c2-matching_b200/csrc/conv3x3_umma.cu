@@ -545,6 +545,7 @@ extern "C" int c2m_conv3x3(const c2m_conv3x3_args *a, c2m_stream_t stream) {
     }
     p.stacked = 1;
     p.dbg = 0;
+    p.cs = 0;
     if (const char *ev = getenv("C2M_CONV_DBG")) p.dbg = atoi(ev);
     p.n_st = ceil_div(p.tiles_x * p.tiles_y, p.T);
     p.act = a->act; p.sa_in = a->sa_in; p.sa_res = a->sa_res; p.sa_out = a->sa_out;

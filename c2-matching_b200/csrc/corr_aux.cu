@@ -181,7 +181,8 @@ __global__ void __launch_bounds__(256) search_generic_kernel(const float *__rest
     __shared__ int qpix[GS_T];
     __shared__ int rpix[GS_T];
     __shared__ float rsc[GS_T];
-    __shared__ Candidate red[GS_T][16];          // 32 KB
+    struct Red { float v[CORR_TOPK]; int i[CORR_TOPK]; float dropped; };      // 36 B
+    __shared__ Red red[GS_T][16];
 
     const int b = blockIdx.z, chunk = blockIdx.y;
     const int q0 = blockIdx.x * GS_T;
@@ -197,10 +198,10 @@ __global__ void __launch_bounds__(256) search_generic_kernel(const float *__rest
     const int per = ceil_div(ceil_div(g.NR, GS_T), nchunk) * GS_T;
     const int r_begin = chunk * per, r_end = min(g.NR, r_begin + per);
 
-    float cv[4][CORR_TOPK];
+    float cv[4][CORR_TOPK], cdrop[4];
     int ci[4][CORR_TOPK];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) cand_init(cv[i], ci[i]);
+    for (int i = 0; i < 4; ++i) { cand_init(cv[i], ci[i]); cdrop[i] = -INFINITY; }
 
     const int lrow = t >> 1 & 63, lhalf = t & 1;     // loader: threads 0..127 -> A, 128..255 -> B
     for (int r0 = r_begin; r0 < r_end; r0 += GS_T) {
@@ -254,30 +255,32 @@ __global__ void __launch_bounds__(256) search_generic_kernel(const float *__rest
             if (r < r_end) {
                 const float sc = rsc[tx * 4 + j];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) cand_push(acc[i][j] * sc, r, cv[i], ci[i]);
+                for (int i = 0; i < 4; ++i) cand_push(acc[i][j] * sc, r, cv[i], ci[i], cdrop[i]);
             }
         }
     }
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        Candidate c;
+        Red c;
 #pragma unroll
         for (int k = 0; k < CORR_TOPK; ++k) { c.v[k] = cv[i][k]; c.i[k] = ci[i][k]; }
+        c.dropped = cdrop[i];
         red[ty * 4 + i][tx] = c;
     }
     __syncthreads();
     if (t < GS_T && q0 + t < g.NQ) {
-        float av[CORR_TOPK];
+        float av[CORR_TOPK], adrop = -INFINITY;
         int ai[CORR_TOPK];
         cand_init(av, ai);
         for (int k = 0; k < 16; ++k) {
-            const Candidate c = red[t][k];
+            const Red c = red[t][k];
+            adrop = fmaxf(adrop, c.dropped);
 #pragma unroll
             for (int j = 0; j < CORR_TOPK; ++j)
-                if (c.i[j] != 0x7fffffff) cand_push(c.v[j], c.i[j], av, ai);
+                if (c.i[j] != 0x7fffffff) cand_push(c.v[j], c.i[j], av, ai, adrop);
         }
-        part[((size_t)b * nchunk + chunk) * g.NQ + q0 + t] = cand_pack(av, ai);
+        part[((size_t)b * nchunk + chunk) * g.NQ + q0 + t] = cand_pack(av, ai, adrop);
     }
 }
 
@@ -408,18 +411,11 @@ __global__ void __launch_bounds__(256) rescore_kernel(const float *__restrict__ 
     const float window = window_coef * qn * (is_norm ? 1.f : __uint_as_float(*max_pn_bits)) + 1e-30f;
     const float thr = vmax - window;
 
-    // chunks whose LAST list entry is inside the window may hide further candidates -> exhaustive re-scan
+    // a chunk's list is complete unless something it left behind (`dropped`) reaches the window -> exhaustive re-scan
     unsigned ovf_mask = 0;
-#pragma unroll
-    for (int k = 0; k < CORR_TOPK; ++k) {
-        const int slot = lane + 32 * k;
-        const bool hit = (slot % CORR_TOPK) == CORR_TOPK - 1 && ci[k] >= 0 && cv[k] >= thr;
-        unsigned m = __ballot_sync(0xffffffffu, hit);
-        while (m) {
-            const int l = __ffs(m) - 1;
-            m &= m - 1;
-            ovf_mask |= 1u << ((l + 32 * k) / CORR_TOPK);
-        }
+    {
+        const bool hit = lane < nchunk && part[((size_t)b * nchunk + lane) * g.NQ + q].dropped >= thr;
+        ovf_mask = __ballot_sync(0xffffffffu, hit);
     }
 
     float best = -INFINITY;

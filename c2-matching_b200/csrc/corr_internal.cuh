@@ -22,6 +22,8 @@ constexpr int CORR_TOPK = 4;      // candidates kept per (query, Ref chunk) by t
 struct __align__(16) Candidate {
     float v[CORR_TOPK];           // approximate scores, best first
     int i[CORR_TOPK];             // Ref patch indices (-1 = empty slot)
+    float dropped;                // largest approximate score of the chunk that is NOT in the list
+    float pad[3];
 };
 
 struct CorrGeom {
@@ -63,18 +65,21 @@ struct CorrWorkspace {
     size_t total_bytes;
 };
 
-// lexicographic "better": larger score, then lower Ref index
-__device__ __forceinline__ bool cand_better(float s, int r, float v, int i) {
-    return s > v || (s == v && r < i);
-}
-// sorted top-4 insert; the common case (not better than the 4th) costs one lexicographic compare
-__device__ __forceinline__ void cand_push(float s, int r, float (&v)[CORR_TOPK], int (&i)[CORR_TOPK]) {
-    if (!cand_better(s, r, v[3], i[3])) return;
-    if (cand_better(s, r, v[2], i[2])) {
+// Sorted top-4 insert with a record of what falls off the list: `dropped` ends up as the largest score the chunk
+// produced that is not in v[] (scores that never made it, and entries pushed out).  Strict '>' — ties beyond the
+// list count as dropped, and the rescoring pass re-scans a chunk exhaustively whenever `dropped` reaches the
+// window, so neither ties nor the list length can lose the true argmax.
+__device__ __forceinline__ void cand_push(float s, int r, float (&v)[CORR_TOPK], int (&i)[CORR_TOPK], float &dropped) {
+    if (!(s > v[3])) {
+        dropped = fmaxf(dropped, s);
+        return;
+    }
+    dropped = fmaxf(dropped, v[3]);
+    if (s > v[2]) {
         v[3] = v[2]; i[3] = i[2];
-        if (cand_better(s, r, v[1], i[1])) {
+        if (s > v[1]) {
             v[2] = v[1]; i[2] = i[1];
-            if (cand_better(s, r, v[0], i[0])) {
+            if (s > v[0]) {
                 v[1] = v[0]; i[1] = i[0]; v[0] = s; i[0] = r;
             } else {
                 v[1] = s; i[1] = r;
@@ -90,11 +95,16 @@ __device__ __forceinline__ void cand_init(float (&v)[CORR_TOPK], int (&i)[CORR_T
 #pragma unroll
     for (int k = 0; k < CORR_TOPK; ++k) { v[k] = -INFINITY; i[k] = 0x7fffffff; }
 }
-__device__ __forceinline__ Candidate cand_pack(const float (&v)[CORR_TOPK], const int (&i)[CORR_TOPK]) {
+__device__ __forceinline__ Candidate cand_pack(const float (&v)[CORR_TOPK], const int (&i)[CORR_TOPK], float dropped) {
     Candidate c;
 #pragma unroll
     for (int k = 0; k < CORR_TOPK; ++k) { c.v[k] = v[k]; c.i[k] = i[k] == 0x7fffffff ? -1 : i[k]; }
+    c.dropped = dropped;
+    c.pad[0] = c.pad[1] = c.pad[2] = 0.f;
     return c;
+}
+__device__ __forceinline__ bool cand_better(float s, int r, float v, int i) {   // exact scores: lower index wins ties
+    return s > v || (s == v && r < i);
 }
 
 // (score, index) packed so that an unsigned 64-bit max is the lexicographic "better": larger score, then LOWER index

@@ -49,7 +49,7 @@ constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);   // hi+lo of both sides = 
 constexpr int NSTAGE = 3;
 constexpr int UM = TQ_R * BW, UN = TR_R * BW;      // 128, 256
 constexpr int TMEM_COLS = 512;
-constexpr int SMEM_AUX = 2 * UN * 8 + 128;         // (scale, index) per column, double buffered, + barriers
+constexpr int SMEM_AUX = 2 * UN * 8 + 128;         // (scale, bias) per column, double buffered, + barriers
 constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + SMEM_AUX + 1024;
 static_assert(A_BYTES % 128 == 0 && B_BYTES % 128 == 0, "TMA destinations must stay 128B aligned");
 static_assert(UM == 128 && UN == 256, "tile shape is tied to the UMMA instruction shape");
@@ -71,7 +71,7 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap tm_in_hi, const __grid_cons
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *aux = smem + NSTAGE * STAGE_BYTES;
-    float2 *rcol = reinterpret_cast<float2 *>(aux);                 // [2][UN] (score scale, Ref index bits or -1)
+    float2 *rcol = reinterpret_cast<float2 *>(aux);                 // [2][UN] (score scale, bias)
     uint64_t *bars = reinterpret_cast<uint64_t *>(aux + 2 * UN * 8);
     uint64_t *full = bars, *empty = bars + NSTAGE, *tfull = bars + 2 * NSTAGE, *tempty = bars + 2 * NSTAGE + 2;
     uint32_t *tmem_base_p = reinterpret_cast<uint32_t *>(bars + 2 * NSTAGE + 4);
@@ -168,6 +168,11 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap tm_in_hi, const __grid_cons
         }
     } else if (warp >= 4) {
         // ================================ epilogue =========================================
+        // Branch-free inner loop (the per-score compare-and-insert of the first version kept the tensor pipe at
+        // 38 %): per 32-column block (two Ref block rows, 28 valid scores) only min / max run per score —
+        // m1 = block best, m2 = block second best — and just the block winner is offered to the top-4 list.
+        // Everything that is not in the list (block runners-up, evicted entries) feeds `dropped`, the largest score
+        // left behind; the rescoring pass re-scans the chunk exhaustively when `dropped` reaches its window.
         const int e = threadIdx.x - 128;                    // 0..127 = accumulator row m = 16 * block row + block column
         const int quarter = warp & 3;
         const int yy = e >> 4, xx = e & 15;
@@ -181,27 +186,30 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap tm_in_hi, const __grid_cons
             float cv[CORR_TOPK];
             int ci[CORR_TOPK];
             cand_init(cv, ci);
+            float dropped = -INFINITY;
             for (int rt = rt_b; rt < rt_e; ++rt) {
                 const int ry0 = (rt / p.rt_x) * TR_R, rx0 = (rt % p.rt_x) * TV;
-                float2 *rc = rcol + acc * UN;
+                float2 *rc = rcol + acc * UN;               // per column: score = V * scale + bias (bias = -inf: no such patch)
 #pragma unroll
                 for (int k = 0; k < UN / 128; ++k) {
                     const int n = e + k * 128;
                     const int uu = n >> 4, vv = n & 15;
                     const int ry = ry0 + uu, rx = rx0 + vv;
                     const bool ok = vv < TV && ry < p.rh && rx < p.rw;
-                    const int r = ry * p.rw + rx;
-                    rc[n] = make_float2(ok ? rinvb[r] * sinv : 0.f, __int_as_float(ok ? r : -1));
+                    rc[n] = ok ? make_float2(rinvb[ry * p.rw + rx] * sinv, 0.f) : make_float2(0.f, -INFINITY);
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 mbar_wait(&tfull[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * UN;
+                const uint32_t rc_s = smem_u32(rc);
 #pragma unroll 1
                 for (int cc = 0; cc < UN / 32; ++cc) {      // 32 columns = two Ref block rows
                     uint32_t reg[32];
                     tmem_ld_32x32(taddr + cc * 32, reg);
                     tmem_ld_wait();
+                    float sv[2 * TV];
+                    float m1 = -INFINITY, m2 = -INFINITY;
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
 #pragma unroll
@@ -210,11 +218,22 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap tm_in_hi, const __grid_cons
                             // column taps: lane m+dx, column n+dx hold V(q + (0,dx), r + (0,dx))
                             const float t1 = __shfl_down_sync(0xffffffffu, __uint_as_float(reg[j + 1]), 1);
                             const float t2 = __shfl_down_sync(0xffffffffu, __uint_as_float(reg[j + 2]), 2);
-                            const float sc = (__uint_as_float(reg[j]) + t1) + t2;
-                            const float2 c = rc[cc * 32 + j];
-                            const int r = __float_as_int(c.y);
-                            if (r >= 0) cand_push(sc * c.x, r, cv, ci);
+                            float cx, cy;
+                            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(cx), "=f"(cy) : "r"(rc_s + (cc * 32 + j) * 8));
+                            const float sc = fmaf((__uint_as_float(reg[j]) + t1) + t2, cx, cy);
+                            sv[hh * TV + v] = sc;
+                            m2 = fmaxf(m2, fminf(m1, sc));
+                            m1 = fmaxf(m1, sc);
                         }
+                    }
+                    dropped = fmaxf(dropped, m2);
+                    if (m1 > cv[3]) {                        // rare once the list has warmed up
+                        int jw = 0;
+#pragma unroll
+                        for (int k = 2 * TV - 1; k >= 0; --k)
+                            if (sv[k] == m1) jw = (k / TV) * 16 + k % TV;         // lowest column among equals
+                        const int r = (ry0 + cc * 2 + (jw >> 4)) * p.rw + rx0 + (jw & 15);
+                        cand_push(m1, r, cv, ci, dropped);
                     }
                 }
                 tc_fence_before();
@@ -223,7 +242,7 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap tm_in_hi, const __grid_cons
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
             if (xx < TV && qy < p.gh && qx < p.gw)
-                part[((size_t)b * p.nchunk + chunk) * p.NQ + qy * p.gw + qx] = cand_pack(cv, ci);
+                part[((size_t)b * p.nchunk + chunk) * p.NQ + qy * p.gw + qx] = cand_pack(cv, ci, dropped);
         }
     }
 

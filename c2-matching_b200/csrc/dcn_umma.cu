@@ -60,7 +60,9 @@ struct DcnTc {
     int n_ko;                  // real K octets = C/8 * 9
     int L, lshift;             // K octets per gather thread and stage (1, 2 or 4), log2
     int opp_shift;             // log2(opp) when opp is a power of two, else -1 (then L == 1)
-    int nstage, nbst;          // ring depths (activation stages, weight chunks)
+    int nstage, nbst;          // ring depths (activation stages, weight chunks); powers of two
+    int nstage_shift;          // log2(nstage)
+    int tg;                    // pixel tiles per work item (<= T)
     int sc_shift;              // log2(pre_scale) when the flow table is used (idx given, scale in {1,2,4,8}), else -1
     int tab_h, tab_w;          // flow-table cells per tile: 16/s + 2, 8/s + 2
     float inv_ref_gw, inv_scale;   // reciprocals for the exact float-assisted integer divisions
@@ -124,12 +126,15 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_img = p.tiles_x * p.tiles_y;
-    // Work = flat list of (Cout slice, image, pixel tile); every CTA owns one contiguous, evenly sized range
-    // of it and walks the range in groups of <= T tiles that share the streamed weight chunks.
+    // Work = flat list of (image, pixel tile), cut into items of Tg consecutive tiles (they share the streamed weight
+    // chunks); item i runs on CTA i % grid.  At any moment the CTAs therefore work on ~grid * Tg CONSECUTIVE tiles —
+    // a third of one image at the largest layer — so the gathered input map of ONE image (105 MB) is what has to
+    // stay in L2, not the whole batch (contiguous per-CTA ranges spread the CTAs over all images at once: ncu showed
+    // 7.3 GB of DRAM reads for 2.3 GB of algorithmic traffic).  Tg shrinks for small problems so all SMs get work.
     const int TT = p.B * tiles_img;
-    const int n_work = p.nslice * TT;
-    const int w_begin = (int)((long long)n_work * blockIdx.x / gridDim.x);
-    const int w_end = (int)((long long)n_work * (blockIdx.x + 1) / gridDim.x);
+    const int n_work = TT;
+    const int Tg = d.tg;
+    const int n_items = (n_work + Tg - 1) / Tg;
     const int nacc = p.T;                                // TMEM accumulators, rotated across groups
     const uint32_t need_cols = (uint32_t)p.N * p.T;
     const uint32_t tmem_cols = need_cols <= 32 ? 32 : need_cols <= 64 ? 64 : need_cols <= 128 ? 128
@@ -152,9 +157,9 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
     const uint32_t tmem_base = *tmem_base_p;
     const int sw = *reinterpret_cast<const int *>(q.wblob);
 
-    auto group = [&](int pos, int &slice, int &nt) {
-        slice = pos / TT;
-        nt = min(min(p.T, w_end - pos), (slice + 1) * TT - pos);
+    auto group = [&](int item, int &pos, int &nt) {
+        pos = item * Tg;
+        nt = min(Tg, n_work - pos);
     };
 
     // Register budget per warpgroup.  The CTA's pool is what it was launched with (80 x 768 = 61440):
@@ -166,13 +171,11 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
         // ================================ weight producer ===================================
         if (lane == 0) {
             int bst = 0, bphase = 0;
-            for (int pos = w_begin, nt = 0; pos < w_end; pos += nt) {
-                int slice;
-                group(pos, slice, nt);
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 for (int kc = 0; kc < p.nkc; ++kc) {
                     mbar_wait(&bempty[bst], bphase ^ 1);
                     mbar_arrive_expect_tx(&bfull[bst], w_chunk);
-                    const uint8_t *src = q.wblob + W_HDR + ((size_t)slice * p.nkc + kc) * w_chunk;
+                    const uint8_t *src = q.wblob + W_HDR + (size_t)kc * w_chunk;
                     asm volatile(
                         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                         ::"r"(smem_u32(sW + bst * w_chunk)), "l"(src), "r"(w_chunk), "r"(smem_u32(&bfull[bst]))
@@ -189,9 +192,9 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
             int stage = 0, phase = 0, bst = 0, bphase = 0;
             uint32_t tph = 0;
             int abase = 0;
-            for (int pos = w_begin, nt = 0; pos < w_end; pos += nt) {
-                int slice;
-                group(pos, slice, nt);
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                int pos, nt;
+                group(item, pos, nt);
                 for (int kc = 0; kc < p.nkc; ++kc) {
                     mbar_wait(&bfull[bst], bphase);
                     tc_fence_after();
@@ -239,19 +242,15 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
         const float res_scale = 1.f;
         const float so = ldexpf(1.f, p.sa_out);
         uint32_t tph = 0;
-        int abase = 0, cur_slice = -1;
-        for (int pos = w_begin, nt = 0; pos < w_end; pos += nt) {
-            int slice;
-            group(pos, slice, nt);
-            const int o_base = slice * p.N;
-            if (slice != cur_slice) {                      // uniform over the 4 epilogue warps
-                cur_slice = slice;
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                for (int i = e; i < p.N; i += 128) sbias[i] = (q.bias && o_base + i < p.Cout) ? q.bias[o_base + i] : 0.f;
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-            }
+        int abase = 0;
+        for (int i = e; i < p.N; i += 128) sbias[i] = (q.bias && i < p.Cout) ? q.bias[i] : 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int o_base = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            int pos, nt;
+            group(item, pos, nt);
             for (int t = 0; t < nt; ++t) {
-                const int r = pos + t - slice * TT;
+                const int r = pos + t;
                 const int b = r / tiles_img, tt = r - b * tiles_img;
                 const int y = (tt / p.tiles_x) * T_R + e / T_C, x = (tt % p.tiles_x) * T_C + e % T_C;
                 const bool ok = y < p.H && x < p.W;
@@ -275,29 +274,32 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
         // 4 thread groups of 128 (thread = pixel m of the tile).  With L K-octets per thread a stage has NS = 4 / L
         // thread slots, so the 4 groups split into NG = L stage groups that work on consecutive stages concurrently:
         // group grp -> (stage residue sg = grp / NS, slot = grp % NS); slot covers octets [slot*L, slot*L + L).
+        // All index arithmetic is 32-bit (the host checks the map sizes); everything that depends only on the
+        // K chunk (group, tap, operand plane offsets) is recomputed when kc changes, not per pixel.
         const int g_tid = threadIdx.x - 256;
         const int m = g_tid & 127;
         const int grp = g_tid >> 7;
         const int L = d.L, NG = L, NS = KOCT >> d.lshift;
         const int sg = grp / NS, slot = grp - sg * NS;
-        const int P = p.H * p.W;
+        const int P = p.H * p.W, W8 = p.W * 8;
         const int mrow = m / T_C, mcol = m % T_C;
         const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
-        const size_t x_img = (size_t)d.C8 * P * 8;
+        const int x_img = d.C8 * P * 8;                       // elements per image of one operand half (< 2^31, host-checked)
+        const int om_img = (d.om_c8 > 0 ? d.om_c8 * 8 : (d.mask ? 2 : 3) * d.dg * 9) * P;
         const int om_mask_base = 2 * d.dg * 9;
         const int tab_n = d.tab_h * d.tab_w;
         // cell of this thread's pixel inside a tile's flow table, before the tap shift (+2 halo cells)
         const int cell0 = d.sc_shift >= 0 ? ((mrow >> d.sc_shift) + 2) * d.tab_w + (mcol >> d.sc_shift) + 2 : 0;
+        const float Hf = (float)p.H, Wf = (float)p.W;
         struct Meta { float off_h, off_w, mr; };
         int ring = 0;                                       // stages issued by this CTA so far (all groups agree)
         int gi = 0;                                         // tile-group counter (table double buffer)
-        for (int pos = w_begin, nt = 0; pos < w_end; pos += nt, ++gi) {
-            int slice;
-            group(pos, slice, nt);
-            const int r0g = pos - slice * TT;               // (image, tile) index of the group's first tile
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++gi) {
+            int r0g, nt;                                    // (image, tile) index of the group's first tile, tiles
+            group(item, r0g, nt);
             const int n_steps = p.nkc * nt;
             int4 *tinfo = tile_info + (gi & 1) * MAXT;
-            float2 *tab = flow_tab + (size_t)(gi & 1) * p.T * tab_n;
+            float2 *tab = flow_tab + (gi & 1) * p.T * tab_n;
 
             // ---- per tile group: tile origins and the decoded flow of every index-map cell a tile can touch
             if (g_tid < nt) {
@@ -325,48 +327,70 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
             }
             asm volatile("bar.sync 2, 512;" ::: "memory");
 
+            // ---- constants of K chunk kc for this thread's octet run
+            int c_kc = -1, c_ki = 0, c_kj = 0, c_tap = 0, c_tapcell = 0, c_off = 0, c_moff = 0, c_xoff = 0;
+            bool c_valid = false;
+            float c_fy = 0.f, c_fx = 0.f;
+            auto set_kc = [&](int kc) {
+                c_kc = kc;
+                const int ko = kc * KOCT + slot * L;
+                c_valid = ko < d.n_ko;
+                const int pair = d.opp_shift >= 0 ? (ko >> d.opp_shift) : ko / d.opp;
+                const int g = pair / 9;
+                c_tap = pair - g * 9;
+                c_ki = c_tap / 3;
+                c_kj = c_tap - c_ki * 3;
+                c_fy = (float)(c_ki - 1);
+                c_fx = (float)(c_kj - 1);
+                c_tapcell = c_ki * d.tab_w + c_kj;
+                if (d.om_c8 > 0) {     // octet-planar: channel c of pixel pp lives at ((c >> 3) * P + pp) * 8 + (c & 7)
+                    const int c0 = 2 * pair, cm = om_mask_base + pair;
+                    c_off = (c0 >> 3) * P * 8 + (c0 & 7);
+                    c_moff = (cm >> 3) * P * 8 + (cm & 7);
+                } else {
+                    c_off = 2 * pair * P;
+                    c_moff = (d.mask ? pair : om_mask_base + pair) * P;
+                }
+                // first channel octet of this run: group g, octets [ko - pair * opp, +L) of the group
+                c_xoff = (g * d.opp + (ko - (d.opp_shift >= 0 ? (pair << d.opp_shift) : pair * d.opp))) * P * 8;
+            };
+
             // ---- metadata of unit (kc, t): raw offsets (+ pre-offset) and mask logit of this thread's pixel
-            auto fetch = [&](int kc, int t, bool in_range, Meta &mt, int &pair_out, int &y_out, int &x_out, int &b_out,
-                             bool &live) {
+            auto fetch = [&](int kc, int t, bool in_range, Meta &mt, int &y_out, int &x_out, int &b_out, bool &live) {
                 mt.off_h = mt.off_w = mt.mr = 0.f;
-                pair_out = 0; y_out = x_out = b_out = 0;
+                y_out = x_out = b_out = 0;
                 live = false;
                 if (!in_range) return;
+                if (kc != c_kc) set_kc(kc);
                 const int4 ti = tinfo[t];
                 const int b = ti.x, y = ti.y + mrow, xx = ti.z + mcol;
-                const int ko = kc * KOCT + slot * L;
-                live = y < p.H && xx < p.W && ko < d.n_ko;
-                pair_out = d.opp_shift >= 0 ? (ko >> d.opp_shift) : ko / d.opp;
+                live = c_valid && y < p.H && xx < p.W;
                 y_out = y; x_out = xx; b_out = b;
                 if (!live) return;
-                const int g = pair_out / 9, tap = pair_out - g * 9;
-                const int jj = pair_out, pp = y * p.W + xx;
-                if (d.om_c8 > 0) {     // 2jj is even: the (y, x) offset pair shares an octet
-                    const float *ob = d.om + (size_t)b * d.om_c8 * P * 8;
-                    const int c0 = 2 * jj, cm = om_mask_base + jj;
-                    const float2 of = ldg_stream_f2(ob + ((size_t)(c0 >> 3) * P + pp) * 8 + (c0 & 7), pol_stream);
+                const int pp = y * p.W + xx;
+                const float *omb = d.om + (size_t)b * om_img;
+                if (d.om_c8 > 0) {     // the (y, x) offset pair shares an octet: one 8-byte load
+                    const float2 of = ldg_stream_f2(omb + c_off + pp * 8, pol_stream);
                     mt.off_h = of.x;
                     mt.off_w = of.y;
-                    mt.mr = ldg_stream_f1(ob + ((size_t)(cm >> 3) * P + pp) * 8 + (cm & 7), pol_stream);
+                    mt.mr = ldg_stream_f1(omb + c_moff + pp * 8, pol_stream);
                 } else {
-                    const float *omb = d.om + (size_t)b * (d.mask ? 2 : 3) * d.dg * 9 * P;
-                    mt.off_h = ldg_stream_f1(omb + (size_t)(2 * jj) * P + pp, pol_stream);
-                    mt.off_w = ldg_stream_f1(omb + (size_t)(2 * jj + 1) * P + pp, pol_stream);
-                    mt.mr = d.mask ? ldg_stream_f1(d.mask + ((size_t)b * d.dg * 9 + jj) * P + pp, pol_stream)
-                                   : ldg_stream_f1(omb + (size_t)(om_mask_base + jj) * P + pp, pol_stream);
+                    mt.off_h = ldg_stream_f1(omb + c_off + pp, pol_stream);
+                    mt.off_w = ldg_stream_f1(omb + c_off + P + pp, pol_stream);
+                    mt.mr = d.mask ? ldg_stream_f1(d.mask + (size_t)b * (d.dg * 9 * P) + c_moff + pp, pol_stream)
+                                   : ldg_stream_f1(omb + c_moff + pp, pol_stream);
                 }
-                const int ki = tap / 3, kj = tap - ki * 3;
                 if (d.pre) {
-                    const float2 pq = *reinterpret_cast<const float2 *>(d.pre + (((size_t)b * 9 + tap) * P + pp) * 2);
+                    const float2 pq = *reinterpret_cast<const float2 *>(d.pre + ((size_t)(b * 9 + c_tap) * P + pp) * 2);
                     mt.off_w += pq.x;
                     mt.off_h += pq.y;
                 } else if (d.sc_shift >= 0) {
-                    const float2 fl = tab[t * tab_n + cell0 - ki * d.tab_w - kj];
+                    const float2 fl = tab[t * tab_n + cell0 - c_tapcell];
                     mt.off_w += fl.x;
                     mt.off_h += fl.y;
                 } else if (d.idx) {                       // scales the table does not cover: decode in place
                     const int sc = d.pre_scale;
-                    const int ys = y - sc * ki, xs = xx - sc * kj;
+                    const int ys = y - sc * c_ki, xs = xx - sc * c_kj;
                     if (ys >= 0 && xs >= 0) {
                         const int yy = fast_div(ys, sc, d.inv_scale), xg = fast_div(xs, sc, d.inv_scale);
                         if (yy < d.gh && xg < d.gw) {
@@ -383,53 +407,50 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
             int kc = 0, t = sg;
             while (t >= nt) { t -= nt; ++kc; }
             Meta mt, nx;
-            int pr, npr, y, ny, xx, nxx, b, nb;
+            int y, ny, xx, nxx, b, nb;
             bool lv, nlv;
-            fetch(kc, t, sg < n_steps, mt, pr, y, xx, b, lv);
+            fetch(kc, t, sg < n_steps, mt, y, xx, b, lv);
             for (int step = sg; step < n_steps; step += NG) {
                 int nkc_ = kc, nt_ = t + NG;
                 while (nt_ >= nt) { nt_ -= nt; ++nkc_; }
                 // ---- sampling point of the unit's (pixel, g, tap): dcn_v2_im2col_cuda.cu:25-54,172-190
                 int o0 = 0, o1 = 0, o2 = 0, o3 = 0;
                 float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
-                int oct_c = 0;
+                const int xoff = c_xoff;                    // belongs to kc (set_kc(kc) ran in this unit's fetch)
                 if (lv) {
-                    const int g = pr / 9, tap = pr - g * 9, ki = tap / 3, kj = tap - ki * 3;
-                    const float h_im = (float)(y - 1 + ki) + mt.off_h;
-                    const float w_im = (float)(xx - 1 + kj) + mt.off_w;
-                    if (h_im > -1.f && w_im > -1.f && h_im < (float)p.H && w_im < (float)p.W) {
-                        const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
-                        const int h_high = h_low + 1, w_high = w_low + 1;
-                        const float lh = h_im - h_low, lw = w_im - w_low;
+                    const float h_im = ((float)y + c_fy) + mt.off_h;
+                    const float w_im = ((float)xx + c_fx) + mt.off_w;
+                    if (h_im > -1.f && w_im > -1.f && h_im < Hf && w_im < Wf) {
+                        const float hf = floorf(h_im), wf = floorf(w_im);
+                        const int h_low = (int)hf, w_low = (int)wf;
+                        const float lh = h_im - hf, lw = w_im - wf;
                         const float hh = 1.f - lh, hw = 1.f - lw;
-                        const bool tv = h_low >= 0, bv = h_high <= p.H - 1, lvv = w_low >= 0, rv = w_high <= p.W - 1;
+                        const bool tv = h_low >= 0, bv = h_low + 1 <= p.H - 1, lvv = w_low >= 0, rv = w_low + 1 <= p.W - 1;
                         // sigmoid to ~2 ulp: the TC path is fp32-grade, not bit-exact; the mask is folded into the weights
                         const float mk = d.mask ? mt.mr : __fdividef(1.f, 1.f + __expf(-mt.mr));
-                        const int r0 = (h_low * p.W + w_low) * 8;
-                        if (tv && lvv) { o0 = r0; w0 = hh * hw * mk; }
-                        if (tv && rv) { o1 = r0 + 8; w1 = hh * lw * mk; }
-                        if (bv && lvv) { o2 = r0 + p.W * 8; w2 = lh * hw * mk; }
-                        if (bv && rv) { o3 = r0 + p.W * 8 + 8; w3 = lh * lw * mk; }
+                        const int r0 = h_low * W8 + w_low * 8;
+                        const float mh = hh * mk, ml = lh * mk;
+                        if (tv && lvv) { o0 = r0; w0 = mh * hw; }
+                        if (tv && rv) { o1 = r0 + 8; w1 = mh * lw; }
+                        if (bv && lvv) { o2 = r0 + W8; w2 = ml * hw; }
+                        if (bv && rv) { o3 = r0 + W8 + 8; w3 = ml * lw; }
                     }
-                    // first channel octet of this run: group g, octets [ko - pair * opp, +L) of the group
-                    const int ko = kc * KOCT + slot * L;
-                    oct_c = g * d.opp + (ko - (d.opp_shift >= 0 ? (pr << d.opp_shift) : pr * d.opp));
                 }
-                const __half *xh = d.x_hi + b * x_img + (size_t)oct_c * P * 8;
-                const __half *xl = d.x_lo + b * x_img + (size_t)oct_c * P * 8;
+                const __half *xh = d.x_hi + (size_t)b * x_img + (lv ? xoff : 0);
+                const __half *xl = d.x_lo + (size_t)b * x_img + (lv ? xoff : 0);
                 const __half2 wh0 = __float2half2_rn(w0), wh1 = __float2half2_rn(w1), wh2 = __float2half2_rn(w2),
                               wh3 = __float2half2_rn(w3);
                 const int stage_idx = ring + step;
                 const int rs = stage_idx & nstage_mask;
-                const uint32_t rphase = (uint32_t)(stage_idx >> (31 - __clz(d.nstage))) & 1u;
+                const uint32_t rphase = (uint32_t)(stage_idx >> d.nstage_shift) & 1u;
                 uint8_t *sdst = sA + rs * A_STAGE + (slot * L) * A_OCT_B + m * 16;
                 // next unit's metadata goes out before this unit's corner fetches come back
-                fetch(nkc_, nt_, step + NG < n_steps, nx, npr, ny, nxx, nb, nlv);
+                fetch(nkc_, nt_, step + NG < n_steps, nx, ny, nxx, nb, nlv);
 #pragma unroll 1
                 for (int u = 0; u < L; ++u) {
                     // octet-planar operand: the 32 lanes of a warp (4 rows x 8 pixels) read 16 B each from runs of
                     // adjacent pixels (8 lines per request instead of 32 with a channels-last fp32 input)
-                    const size_t po = (size_t)u * P * 8;
+                    const int po = u * P * 8;
                     const uint4 ch0 = ldg_keep_v4(xh + po + o0, pol_keep), ch1 = ldg_keep_v4(xh + po + o1, pol_keep);
                     const uint4 ch2 = ldg_keep_v4(xh + po + o2, pol_keep), ch3 = ldg_keep_v4(xh + po + o3, pol_keep);
                     const uint4 cl0 = ldg_keep_v4(xl + po + o0, pol_keep), cl1 = ldg_keep_v4(xl + po + o1, pol_keep);
@@ -454,9 +475,9 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
                         const float vx = fmaf(w0, a.x, fmaf(w1, bq.x, fmaf(w2, cq.x, fmaf(w3, dq.x, lf.x))));
                         const float vy = fmaf(w0, a.y, fmaf(w1, bq.y, fmaf(w2, cq.y, fmaf(w3, dq.y, lf.y))));
                         const __half2 hq = __floats2half2_rn(vx, vy);
-                        const float2 hf = __half22float2(hq);
+                        const float2 hf2 = __half22float2(hq);
                         h4[j] = hq;
-                        l4[j] = __floats2half2_rn(vx - hf.x, vy - hf.y);
+                        l4[j] = __floats2half2_rn(vx - hf2.x, vy - hf2.y);
                     }
                     if (u == 0) mbar_wait(&empty[rs], rphase ^ 1u);
                     *reinterpret_cast<uint4 *>(sdst + u * A_OCT_B) = *reinterpret_cast<const uint4 *>(h4);
@@ -465,7 +486,7 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full[rs]);
-                mt = nx; pr = npr; lv = nlv; y = ny; xx = nxx; b = nb;
+                mt = nx; lv = nlv; y = ny; xx = nxx; b = nb;
                 kc = nkc_;
                 t = nt_;
             }
@@ -581,6 +602,7 @@ extern "C" int c2m_dcn_v2_fused_tc(const c2m_dcn_tc_args *a, c2m_stream_t stream
     p.ps = 0;
     p.stacked = 0;
     p.dbg = 0;
+    p.cs = 1;
     p.C8out = (a->Cout + 7) / 8; p.Hout = a->H; p.Wout = a->W;
     p.os_b = a->os_b; p.os_c = a->os_c; p.os_y = a->os_y; p.os_x = a->os_x;
     p.f32_mode = a->out_f32 ? f32_store_mode(a->out_f32, nullptr, a->os_b, a->os_c, a->os_y, a->os_x) : 0;
@@ -624,6 +646,7 @@ extern "C" int c2m_dcn_v2_fused_tc(const c2m_dcn_tc_args *a, c2m_stream_t stream
     // ring depths (powers of two): with L octets per thread, L stage groups fill consecutive stages concurrently
     const size_t w_chunk = (size_t)2 * KOCT * p.N * 16;
     d.nstage = d.L == 1 ? 4 : 8;
+    d.nstage_shift = d.L == 1 ? 2 : 3;
     const size_t fixed = (size_t)d.nstage * A_STAGE + (2 * MAX_NSTAGE + 2 * MAX_NBST + 2 * MAXT) * 8 + 16 + 256 * 4 +
                          2 * MAXT * 16 + (size_t)2 * p.T * d.tab_h * d.tab_w * 8 + 1024 + 128;
     d.nbst = fixed + 4 * w_chunk <= 227 * 1024 ? 4 : 2;
@@ -633,14 +656,19 @@ extern "C" int c2m_dcn_v2_fused_tc(const c2m_dcn_tc_args *a, c2m_stream_t stream
     int dev = 0, sms = 0;
     C2M_CUDA(cudaGetDevice(&dev));
     C2M_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const long long n_work = (long long)a->B * p.tiles_x * p.tiles_y * p.nslice;
+    const long long n_work = (long long)a->B * p.tiles_x * p.tiles_y;
     C2M_CHECK_ARG(n_work < (1 << 23), "dcn_v2_fused_tc: too many pixel tiles");
+    // tiles per work item: all T accumulators when there is plenty of work, fewer so that every SM gets an item otherwise
+    d.tg = (int)((n_work + sms - 1) / sms);
+    if (d.tg > p.T) d.tg = p.T;
+    if (d.tg < 1) d.tg = 1;
+    const int n_items = (int)((n_work + d.tg - 1) / d.tg);
     // flops = 2*B*Cout*C*9*Ho*Wo; bytes = 4*B*(C*H*W + 3*dg*9*H*W + Cout*H*W) + weights
     const double px = (double)a->B * a->H * a->W;
     const double flops = 2.0 * a->Cout * a->C * 9.0 * px;
     const double bytes = 4.0 * px * (a->C + 27.0 * a->dg + a->Cout) + 4.0 * a->Cout * (a->C * 9.0 + 1.0);
     void *ph = prof_begin(PROF_DCN, flops, bytes, st);
-    dcn_umma_kernel<<<n_work < sms ? (int)n_work : sms, NTHREADS, smem, st>>>(q, p, d);
+    dcn_umma_kernel<<<n_items < sms ? n_items : sms, NTHREADS, smem, st>>>(q, p, d);
     C2M_LAUNCH_CHECK("dcn_umma_kernel");
     prof_end(ph, st);
     return C2M_OK;

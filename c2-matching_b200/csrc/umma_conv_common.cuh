@@ -19,6 +19,8 @@ struct ConvParams {
     int ps;                   // 0 or 2: PixelShuffle(2) applied to the PSA output
     int stacked;              // 1: accumulator has 2N columns, value = col[c] + col[N + c]
     int dbg;                  // tuning experiments only (C2M_CONV_DBG): 1 = no global stores, 2 = no TMA reloads
+    int cs;                   // 1: PSA output stored with st.global.cs (streaming: the DCN output must not evict the
+                              // gathered input map from L2)
     int C8out, Hout, Wout;    // geometry of the PSA output tensor
     long long os_b, os_c, os_y, os_x;   // fp32 output element strides
     int f32_mode;             // fp32 output: 0 strided scalar stores, 1 strided with os_c == 1 (16 B stores),
@@ -180,8 +182,13 @@ __device__ __forceinline__ void epilogue_store_block(const ConvPtrs &q, const Co
                                     h8[j] = hh;
                                     l8[j] = __float2half_rn(vs - __half2float(hh));
                                 }
-                                *reinterpret_cast<uint4 *>(q.out_hi + off) = *reinterpret_cast<const uint4 *>(h8);
-                                *reinterpret_cast<uint4 *>(q.out_lo + off) = *reinterpret_cast<const uint4 *>(l8);
+                                if (p.cs) {
+                                    __stcs(reinterpret_cast<uint4 *>(q.out_hi + off), *reinterpret_cast<const uint4 *>(h8));
+                                    __stcs(reinterpret_cast<uint4 *>(q.out_lo + off), *reinterpret_cast<const uint4 *>(l8));
+                                } else {
+                                    *reinterpret_cast<uint4 *>(q.out_hi + off) = *reinterpret_cast<const uint4 *>(h8);
+                                    *reinterpret_cast<uint4 *>(q.out_lo + off) = *reinterpret_cast<const uint4 *>(l8);
+                                }
                             }
                         }
                         if (q.out_hi && p.ps == 2) {

@@ -72,6 +72,17 @@ class RefCUFEDDataset(data.Dataset):
     def __len__(self):
         return len(self.paths)
 
+    def pair_shape(self, i):
+        """(H, W) of the padded HR tensors of pair i, from the image headers only (batch bucketing key)."""
+        from PIL import Image
+        s = self.opt['scale']
+        dims = []
+        for p in self.paths[i]:
+            with Image.open(p) as im:
+                w, h = im.size
+            dims.append((h - h % s, w - w % s))
+        return max(dims[0][0], dims[1][0]), max(dims[0][1], dims[1][1])
+
     def __getitem__(self, i):
         import cv2
         in_path, ref_path = self.paths[i]
@@ -92,6 +103,11 @@ class SyntheticRefDataset(data.Dataset):
 
     def __len__(self):
         return self.num
+
+    def pair_shape(self, i):
+        s = self.opt.get('scale', 4)
+        m = max(self.gt - self.gt % s, self.ref - self.ref % s)
+        return m, m
 
     def __getitem__(self, i):
         rng = np.random.default_rng(1234 + i)

@@ -87,41 +87,99 @@ class RefRestorationModel:
     def optimize_parameters(self, step):
         raise NotImplementedError('training is outside the B200 hot-path scope')
 
-    # -- validation (ref_restoration_model.py:295-370), optionally rank-sharded
-    def validation(self, dataloader, current_iter, tb_logger=None, save_img=False):
+    # -- validation (ref_restoration_model.py:295-370): rank-sharded, batched, host work off the GPU's critical path
+    def _score_image(self, sr, gt, meta, crop, save_dir):
+        """CPU post-processing of one image: tensor2img, un-pad, PNG, PSNR / PSNR_Y / SSIM_Y (reference :306-360)."""
+        sr_img, gt_img = tensor2img([sr, gt])
+        if meta['padding']:
+            oh, ow = meta['original_size']
+            sr_img, gt_img = sr_img[:oh, :ow], gt_img[:oh, :ow]
+        if save_dir is not None:
+            import cv2
+            name = f"{meta['name']}_{self.opt['name']}" + (f"_{self.opt['suffix']}" if self.opt.get('suffix') else '')
+            cv2.imwrite(osp.join(save_dir, name + '.png'), sr_img)
+        psnr = metrics.psnr(sr_img, gt_img, crop_border=crop)
+        sr_y = metrics.bgr2ycbcr(sr_img / 255., only_y=True)
+        gt_y = metrics.bgr2ycbcr(gt_img / 255., only_y=True)
+        psnr_y = metrics.psnr(sr_y * 255, gt_y * 255, crop_border=crop)
+        ssim_y = metrics.ssim(sr_y * 255, gt_y * 255, crop_border=crop)
+        logger.info(f"# img {meta['name']} # PSNR: {psnr:.4e} # PSNR_Y: {psnr_y:.4e} # SSIM_Y: {ssim_y:.4e}.")
+        return (meta['index'], psnr, psnr_y, ssim_y)
+
+    def validation(self, dataloader, current_iter, tb_logger=None, save_img=False, post_workers=None):
+        """The loader hands this rank only ITS pairs (ShardedEvalSampler), batched by shape; per batch the GPU runs
+        one forward, the SR images go to a pinned ring with an async D2H copy, and a thread pool turns them into
+        metrics / PNGs while the next batch is on the GPU.  The ranks' metric rows are all-gathered at the end."""
+        import time
+        from concurrent.futures import ThreadPoolExecutor
         dist_on = torch.distributed.is_available() and torch.distributed.is_initialized()
         rank = torch.distributed.get_rank() if dist_on else 0
-        world = torch.distributed.get_world_size() if dist_on else 1
         crop = self.opt.get('crop_border')
         if crop is None:
             crop = self.opt.get('scale', 4)
-        rows = []
         dataset_name = dataloader.dataset.opt['name']
-        for i, val_data in enumerate(dataloader):
-            if i % world != rank:
-                continue
-            img_name = osp.splitext(osp.basename(val_data['lq_path'][0]))[0]
-            self.feed_data(val_data)
+        save_dir = None
+        if save_img:
+            save_dir = osp.join(self.opt['path']['visualization'], dataset_name)
+            os.makedirs(save_dir, exist_ok=True)
+        batches = getattr(getattr(dataloader, 'batch_sampler', None), 'batches', None)
+        pool = ThreadPoolExecutor(max_workers=int(post_workers or self.opt.get('post_workers') or 4))
+        ring, futures = [], []          # ring of (pinned buffer, in-flight futures using it)
+        depth = 3
+        t_load = t_gpu = 0.0
+        n_img = 0
+        t0 = time.perf_counter()
+        it = iter(dataloader)
+        bi = 0
+        while True:
+            tl = time.perf_counter()
+            try:
+                val_data = next(it)
+            except StopIteration:
+                break
+            t_load += time.perf_counter() - tl
+            tg = time.perf_counter()
+            # the ground truth stays on the host: metrics are computed there (the reference ships it to the GPU and back)
+            self.feed_data({k: v for k, v in val_data.items() if k != 'img_in'})
             self.test()
-            visuals = self.get_current_visuals()
-            sr_img, gt_img = tensor2img([visuals['rlt'], visuals['gt']])
-            if val_data.get('padding') is not None and bool(val_data['padding']):
-                oh, ow = [int(v) for v in val_data['original_size'][:2]]
-                sr_img = sr_img[:oh, :ow]
-                gt_img = gt_img[:oh, :ow]
-            if save_img:
-                import cv2
-                out_dir = osp.join(self.opt['path']['visualization'], dataset_name)
-                os.makedirs(out_dir, exist_ok=True)
-                name = f"{img_name}_{self.opt['name']}" + (f"_{self.opt['suffix']}" if self.opt.get('suffix') else '')
-                cv2.imwrite(osp.join(out_dir, name + '.png'), sr_img)
-            psnr = metrics.psnr(sr_img, gt_img, crop_border=crop)
-            sr_y = metrics.bgr2ycbcr(sr_img / 255., only_y=True)
-            gt_y = metrics.bgr2ycbcr(gt_img / 255., only_y=True)
-            psnr_y = metrics.psnr(sr_y * 255, gt_y * 255, crop_border=crop)
-            ssim_y = metrics.ssim(sr_y * 255, gt_y * 255, crop_border=crop)
-            rows.append((i, psnr, psnr_y, ssim_y))
-            logger.info(f'# img {img_name} # PSNR: {psnr:.4e} # PSNR_Y: {psnr_y:.4e} # SSIM_Y: {ssim_y:.4e}.')
+            out = self.output
+            n = out.shape[0]
+            # pinned slot: reuse the oldest buffer of this shape once its consumers are done
+            slot = None
+            if len(ring) >= depth:
+                buf, futs = ring.pop(0)
+                for f in futs:
+                    f.result()
+                if buf.shape == out.shape:
+                    slot = buf
+            if slot is None:
+                slot = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+            slot.copy_(out, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            t_gpu += time.perf_counter() - tg
+            gts = val_data['img_in']
+            idxs = batches[bi] if batches is not None else list(range(n_img, n_img + n))
+            futs = []
+            for k in range(n):
+                pad = val_data.get('padding')
+                osz = val_data.get('original_size')
+                meta = {'index': int(idxs[k]), 'name': osp.splitext(osp.basename(val_data['lq_path'][k]))[0],
+                        'padding': bool(pad[k]) if pad is not None else False,
+                        'original_size': tuple(int(v) for v in osz[k][:2]) if osz is not None else None}
+
+                def job(k=k, meta=meta, ev=ev, slot=slot, gts=gts):
+                    ev.synchronize()
+                    return self._score_image(slot[k], gts[k], meta, crop, save_dir)
+                futs.append(pool.submit(job))
+            ring.append((slot, futs))
+            futures += futs
+            n_img += n
+            bi += 1
+        rows = [f.result() for f in futures]
+        pool.shutdown()
+        torch.cuda.synchronize(self.device)
+        wall = time.perf_counter() - t0
         t = torch.tensor(rows, dtype=torch.float64, device=self.device).reshape(-1, 4)
         t = gather_rows(t)
         avg = t[:, 1:].mean(0).tolist() if t.numel() else [float('nan')] * 3
@@ -130,5 +188,7 @@ class RefRestorationModel:
             if tb_logger:
                 for k, v in zip(('psnr', 'psnr_y', 'ssim_y'), avg):
                     tb_logger.add_scalar(k, v, current_iter)
-        self.last_validation = {'psnr': avg[0], 'psnr_y': avg[1], 'ssim_y': avg[2], 'n': int(t.shape[0])}
+        self.last_validation = {'psnr': avg[0], 'psnr_y': avg[1], 'ssim_y': avg[2], 'n': int(t.shape[0]),
+                                'rank_images': n_img, 'rank_wall_s': wall, 'rank_loader_wait_s': t_load,
+                                'rank_submit_s': t_gpu}
         return self.last_validation

@@ -56,7 +56,7 @@ def main(argv=None):
     loaders = []
     for phase, dataset_opt in sorted(opt['datasets'].items()):
         test_set = create_dataset(dataset_opt)
-        loaders.append(create_dataloader(test_set, dataset_opt))
+        loaders.append(create_dataloader(test_set, dataset_opt, dist=opt['dist']))     # rank::world shard of the pair list
         logger.info(f"Number of test images in {dataset_opt['name']}: {len(test_set)}")
     model = create_model(opt)
     for loader in loaders:

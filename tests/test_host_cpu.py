@@ -145,7 +145,8 @@ def test_dataset_sample_dict():
     s = next(iter(create_dataloader(ds, {'phase': 'test', 'num_workers': 0})))
     assert tuple(s['img_in_lq'].shape) == (1, 3, 16, 16) and tuple(s['img_ref'].shape) == (1, 3, 64, 64)
     assert s['img_ref'][0, :, 40:, :].abs().sum() == 0 and s['img_ref'][0, :, :, 40:].abs().sum() == 0   # zero pad
-    assert bool(s['padding']) and [int(v) for v in s['original_size']] == [64, 64]
+    # batches keep non-tensor fields as per-sample lists (collate_pairs), so ragged batches of B > 1 pairs work
+    assert s['padding'] == [True] and [tuple(int(v) for v in o) for o in s['original_size']] == [(64, 64)]
 
 
 def test_metrics_and_tensor2img():
@@ -289,3 +290,32 @@ def test_net_map_vgg_defaults_to_imagenet_weights(tmp_path, monkeypatch):
     assert not torch.equal(net3.vgg.vgg_net.conv1_1.weight, tv['features.0.weight'])
     with pytest.raises(FileNotFoundError):
         CorrespondenceGenerationArch(vgg_pretrained_path=str(tmp_path / 'missing.pth'))
+
+
+def test_sharded_eval_sampler_and_shape_buckets():
+    """N1: the pair list is partitioned rank::world at the index level (no rank decodes another rank's pairs, nothing
+    padded or repeated — unlike the training-side DistIterSampler, data_sampler.py:8-69), and same-shape pairs are
+    batched without dropping the ragged tail."""
+    from mmsr.data import create_dataloader, create_dataset
+    from mmsr.data.data_sampler import ShapeBucketBatchSampler, ShardedEvalSampler
+    ds = list(range(126))
+    parts = [list(ShardedEvalSampler(ds, 8, r)) for r in range(8)]
+    assert sorted(sum(parts, [])) == ds and max(map(len, parts)) - min(map(len, parts)) == 1
+    assert parts[3] == list(range(3, 126, 8))
+    shapes = {i: ((320, 480) if i % 3 else (336, 496)) for i in parts[3]}
+    bs = ShapeBucketBatchSampler(parts[3], shapes.__getitem__, 4)
+    got = list(bs)
+    assert sorted(sum(got, [])) == parts[3] and all(len({shapes[i] for i in b}) == 1 and len(b) <= 4 for b in got)
+    assert len(got) == len(bs)
+    # through the factory: synthetic dataset, 2 "ranks", batch 3
+    opt = {'name': 'synth', 'type': 'SyntheticRefDataset', 'num': 7, 'gt_size': 32, 'ref_size': 24, 'num_workers': 0,
+           'batch_size': 3, 'scale': 4}
+    dset = create_dataset(opt)
+    seen = []
+    for r in range(2):
+        loader = create_dataloader(dset, opt, sampler=ShardedEvalSampler(dset, 2, r))
+        for batch in loader:
+            assert batch['img_in_lq'].shape[1:] == (3, 8, 8) and batch['img_ref'].shape[1:] == (3, 32, 32)
+            assert len(batch['lq_path']) == batch['img_in'].shape[0] <= 3
+            seen += batch['lq_path']
+    assert sorted(seen) == [f'synthetic_{i:04d}.png' for i in range(7)]
