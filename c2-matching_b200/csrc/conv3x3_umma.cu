@@ -272,6 +272,256 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// CTA-pair version (cta_group::2, cluster of 2): the 1-CTA kernel above is bound by the tensor core's shared-memory
+// OPERAND FETCH, not by its math (14 KB per K step for 96 cycles of MMA; ncu: tensor pipe 56 % active).  A pair of
+// CTAs issues ONE M = 256 MMA: each CTA feeds its own 128-pixel A tile and only HALF of the B (weight) rows from
+// its own shared memory, so the fetch per CTA and K step drops to 4 + 2 (x_hi * [W_hi|W_lo]) + 4 + 1 (x_lo * W_hi)
+// = 11 KB.  Per-CTA weight rows of one (tap, octet): [0, N) = W_hi (rank 0) / W_lo (rank 1)   -> MMA 1, N_mma = 2N
+//                                                    [N, 1.5N) = W_hi rows [rank*N/2, +N/2)   -> MMA 2, N_mma = N
+// (same offsets in both CTAs, as the instruction requires).  Accumulator layout per CTA is unchanged (128 lanes x
+// 2N stacked columns), so the epilogue is shared with the 1-CTA kernel.
+// Synchronisation: everything the leader's MMA thread waits for lives in the LEADER: full[] / bfull[] have count 2
+// (local TMA + a forwarded arrive from the peer, whose idle MMA warp waits on its local barrier and arrives remotely),
+// tempty[] has count 16 (8 local + 8 remote epilogue warps).  What the MMA thread signals (empty[], bempty[],
+// tfull[]) is committed with .multicast::cluster to the barrier at the same offset in both CTAs.
+// ------------------------------------------------------------------------------------------
+constexpr int NSTAGE2 = 4;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+conv3x3_umma2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+                     const __grid_constant__ CUtensorMap tm2_hi, const __grid_constant__ CUtensorMap tm2_lo,
+                     const ConvPtrs q, const ConvParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t w_rows = p.N + p.N / 2;
+    const uint32_t w_chunk = 9u * KOCT * w_rows * 16;                     // bytes of one chunk in THIS CTA
+    uint8_t *sW = smem;                                                  // [NBST][w_chunk]
+    uint8_t *sA = smem + NBST * w_chunk;                                 // w_chunk is a multiple of 128
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sA + NSTAGE2 * A_STAGE);
+    uint64_t *full = bars, *empty = full + NSTAGE2, *bfull = empty + NSTAGE2, *bempty = bfull + NBST,
+             *tfull = bempty + NBST, *tempty = tfull + MAXT;
+    uint32_t *tmem_base_p = reinterpret_cast<uint32_t *>(tempty + MAXT);
+    float *sbias = reinterpret_cast<float *>(tmem_base_p + 2);           // [N]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int tiles_img = p.tiles_x * p.tiles_y;
+    const int n_items = p.B * p.n_st * p.nslice;          // pair items; n_st = ceil(tiles_img / (2 T))
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const uint32_t need_cols = 2u * p.N * p.T;
+    const uint32_t tmem_cols = need_cols <= 32 ? 32 : need_cols <= 64 ? 64 : need_cols <= 128 ? 128
+                               : need_cols <= 256 ? 256 : 512;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_hi);
+        tma_prefetch_desc(&tm_lo);
+        tma_prefetch_desc(&tm2_hi);
+        tma_prefetch_desc(&tm2_lo);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < NSTAGE2; ++i) { mbar_init(&full[i], leader ? 2 : 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < NBST; ++i) { mbar_init(&bfull[i], leader ? 2 : 1); mbar_init(&bempty[i], 1); }
+        for (int i = 0; i < MAXT; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 16); }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc2(tmem_base_p, tmem_cols);
+        tmem_relinquish2();
+    }
+    tc_fence_before();
+    cluster_sync_all();                                    // both CTAs' barriers exist before anyone signals remotely
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_p;
+    const int sw = *reinterpret_cast<const int *>(q.wblob);              // weight scale exponent
+    const bool w_resident = p.nslice == 1 && p.nkc <= NBST;
+
+    // pair item -> (b, first tile, tiles per CTA, slice); CTA `rank` takes tiles t0 + 2 t + rank (a tile index
+    // beyond the image is a dummy: its TMA box is entirely out of bounds = zeros, its epilogue stores nothing)
+    auto decode = [&](int item, int &b, int &t0, int &nt, int &slice) {
+        slice = item % p.nslice;
+        const int r = item / p.nslice;
+        const int st = r % p.n_st;
+        b = r / p.n_st;
+        t0 = st * 2 * p.T;
+        nt = min(p.T, (tiles_img - t0 + 1) / 2);
+    };
+
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    if (warp == 0) {
+        // ================================ activation producer ===============================
+        if (lane == 0) {
+            int stage = 0, phase = 0;
+            for (int item = pair; item < n_items; item += n_pairs) {
+                int b, t0, nt, slice;
+                decode(item, b, t0, nt, slice);
+                for (int kc = 0; kc < p.nkc; ++kc) {
+                    const bool first = kc < p.nkc_a;
+                    const CUtensorMap *mh = first ? &tm_hi : &tm2_hi, *ml = first ? &tm_lo : &tm2_lo;
+                    const int oct0 = (first ? kc : kc - p.nkc_a) * KOCT;
+                    for (int t = 0; t < nt; ++t) {
+                        const int tt = t0 + 2 * t + (int)rank;
+                        const int y0 = tt < tiles_img ? (tt / p.tiles_x) * T_R : p.H + T_R, x0 = (tt % p.tiles_x) * T_C;
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        uint8_t *s = sA + stage * A_STAGE;
+                        mbar_arrive_expect_tx(&full[stage], A_STAGE);
+                        tma_load_4d(s, mh, &full[stage], (x0 - 1) * 8, y0 - 1, oct0, b);
+                        tma_load_4d(s + A_HALF, ml, &full[stage], (x0 - 1) * 8, y0 - 1, oct0, b);
+                        if (++stage == NSTAGE2) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ================================ weight producer ===================================
+        if (lane == 0) {
+            int bst = 0, bphase = 0;
+            for (int item = pair; item < n_items; item += n_pairs) {
+                int b, t0, nt, slice;
+                decode(item, b, t0, nt, slice);
+                if (w_resident && item != pair) break;
+                for (int kc = 0; kc < p.nkc; ++kc) {
+                    mbar_wait(&bempty[bst], bphase ^ 1);
+                    mbar_arrive_expect_tx(&bfull[bst], w_chunk);
+                    const uint8_t *src = q.wblob + p.w2_off + (((size_t)slice * p.nkc + kc) * 2 + rank) * w_chunk;
+                    for (uint32_t off = 0; off < w_chunk; off += 27648) {
+                        const uint32_t n = min(27648u, w_chunk - off);
+                        asm volatile(
+                            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                            ::"r"(smem_u32(sW + bst * w_chunk + off)), "l"(src + off), "r"(n), "r"(smem_u32(&bfull[bst]))
+                            : "memory");
+                    }
+                    if (++bst == NBST) { bst = 0; bphase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {
+            // ================================ MMA issuer (leader CTA) ==========================
+            const uint32_t idesc = umma_idesc_f16(256, 2 * p.N, 0);
+            const uint32_t idesc_lo = umma_idesc_f16(256, p.N, 0);
+            const uint32_t b_lbo = w_rows * 16;              // next channel octet of the weights
+            int stage = 0, phase = 0, bst = 0, bphase = 0;
+            uint32_t tph = 0;
+            for (int item = pair; item < n_items; item += n_pairs) {
+                int b, t0, nt, slice;
+                decode(item, b, t0, nt, slice);
+                const bool first_item = item == pair;
+                for (int kc = 0; kc < p.nkc; ++kc) {
+                    if (!w_resident || first_item) {
+                        mbar_wait(&bfull[bst], bphase);
+                        tc_fence_after();
+                    }
+                    const uint32_t w_st = smem_u32(sW + bst * w_chunk);
+                    for (int t = 0; t < nt; ++t) {
+                        if (kc == 0) {
+                            mbar_wait(&tempty[t], ((tph >> t) & 1u) ^ 1u);
+                            tc_fence_after();
+                        }
+                        const uint32_t d = tmem_base + t * 2 * p.N;
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t a_hi = smem_u32(sA + stage * A_STAGE);
+                        const uint64_t dah0 = umma_smem_desc(a_hi, A_OCT_B, ROW_B);
+                        const uint64_t dal0 = umma_smem_desc(a_hi + A_HALF, A_OCT_B, ROW_B);
+                        const uint64_t db0 = umma_smem_desc(w_st, b_lbo, 128);               // rows [0, N): MMA 1
+                        const uint64_t db1 = umma_smem_desc(w_st + p.N * 16, b_lbo, 128);    // rows [N, 1.5 N): MMA 2
+#pragma unroll
+                        for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+                            for (int j = 0; j < KOCT / 2; ++j) {
+                                const uint32_t ao = ((tap / 3) * A_C + tap % 3) * 16 + j * 2 * A_OCT_B;
+                                const uint32_t bo = (tap * KOCT + j * 2) * b_lbo;
+                                umma2_f16(d, umma_desc_advance(dah0, ao), umma_desc_advance(db0, bo), idesc, (kc | tap | j) != 0);
+                                umma2_f16(d, umma_desc_advance(dal0, ao), umma_desc_advance(db1, bo), idesc_lo, 1);
+                            }
+                        }
+                        umma_commit2(&empty[stage]);
+                        if (++stage == NSTAGE2) { stage = 0; phase ^= 1; }
+                        if (kc == p.nkc - 1) { umma_commit2(&tfull[t]); tph ^= 1u << t; }
+                    }
+                    if (!w_resident) umma_commit2(&bempty[bst]);
+                    if (++bst == NBST) { bst = 0; bphase ^= 1; }
+                }
+                if (w_resident) { bst = 0; }
+            }
+        } else if (lane == 0) {
+            // ================================ forwarder (peer CTA) =============================
+            // same walk as the issuer: when this CTA's weights / activation stage have landed, tell the leader
+            int stage = 0, phase = 0, bst = 0, bphase = 0;
+            for (int item = pair; item < n_items; item += n_pairs) {
+                int b, t0, nt, slice;
+                decode(item, b, t0, nt, slice);
+                const bool first_item = item == pair;
+                for (int kc = 0; kc < p.nkc; ++kc) {
+                    if (!w_resident || first_item) {
+                        mbar_wait(&bfull[bst], bphase);
+                        mbar_arrive_remote(mapa_u32(smem_u32(&bfull[bst]), 0));
+                    }
+                    for (int t = 0; t < nt; ++t) {
+                        mbar_wait(&full[stage], phase);
+                        mbar_arrive_remote(mapa_u32(smem_u32(&full[stage]), 0));
+                        if (++stage == NSTAGE2) { stage = 0; phase ^= 1; }
+                    }
+                    if (++bst == NBST) { bst = 0; bphase ^= 1; }
+                }
+                if (w_resident) { bst = 0; }
+            }
+        }
+    }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+        // ================================ epilogue ==========================================
+        const int e = (threadIdx.x - 128) & 127;            // pixel of the tile
+        const int quarter = warp & 3;
+        const int c0 = ((warp - 4) >> 2) * 32;
+        const float out_scale = ldexpf(1.f, -(p.sa_in + sw));
+        const float res_scale = ldexpf(1.f, -p.sa_res);
+        const float so = ldexpf(1.f, p.sa_out);
+        const bool has1 = q.res_hi != nullptr;              // warp-uniform
+        uint32_t tph = 0;
+        for (int item = pair; item < n_items; item += n_pairs) {
+            int b, t0, nt, slice;
+            decode(item, b, t0, nt, slice);
+            const int o_base = slice * p.N;
+            asm volatile("bar.sync 1, 256;" ::: "memory");          // previous item's sbias readers are done
+            if (threadIdx.x - 128 < p.N) sbias[threadIdx.x - 128] =
+                (q.bias && o_base + (int)threadIdx.x - 128 < p.Cout) ? q.bias[o_base + threadIdx.x - 128] : 0.f;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            for (int t = 0; t < nt; ++t) {
+                const int tt = t0 + 2 * t + (int)rank;
+                const int y = (tt / p.tiles_x) * T_R + e / T_C, x = (tt % p.tiles_x) * T_C + e % T_C;
+                const bool ok = tt < tiles_img && y < p.H && x < p.W;
+                ResRegs ra;
+                if (has1 && c0 < p.N) prefetch_residual(q.res_hi, q.res_lo, p, b, y, x, ok, o_base, c0, ra);
+                mbar_wait(&tfull[t], (tph >> t) & 1u);
+                tph ^= 1u << t;
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + t * 2 * p.N;
+                if (c0 < p.N)
+                    epilogue_store_block(q, p, taddr, c0, b, y, x, ok, o_base, sbias, out_scale, res_scale, so,
+                                         has1 ? &ra : nullptr);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (leader) mbar_arrive(&tempty[t]);
+                    else mbar_arrive_remote(mapa_u32(smem_u32(&tempty[t]), 0));
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();                                    // nobody leaves while the pair's barriers / TMEM are in use
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc2(tmem_base, tmem_cols);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // PSA <-> strided fp32 converters and the weight pre-pack
 // ------------------------------------------------------------------------------------------
@@ -412,6 +662,33 @@ __global__ void wpack_kernel(const float *__restrict__ w, int Cin, int Cout, int
     }
 }
 
+// CTA-pair layout (after the 1-CTA layout in the same blob): [slice][kc][rank][tap][octet][1.5 N rows][8] fp16,
+// rows [0, N) = W_hi (rank 0) / W_lo (rank 1) of the slice's couts, rows [N, 1.5 N) = W_hi of couts [rank * N/2, +N/2)
+__global__ void wpack2_kernel(const float *__restrict__ w, int Cin, int Cout, int N, int nkc, int nslice,
+                              const uint8_t *__restrict__ blob_hdr, __half *__restrict__ dst) {
+    const float S = ldexpf(1.f, *reinterpret_cast<const int *>(blob_hdr));      // written by wpack_kernel (same stream)
+    const int R = N + N / 2;
+    const long long total = (long long)nslice * nkc * 2 * 9 * KOCT * R * 8;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(e & 7);
+        long long rest = e >> 3;
+        const int row = (int)(rest % R); rest /= R;
+        const int oct = (int)(rest % KOCT); rest /= KOCT;
+        const int tap = (int)(rest % 9); rest /= 9;
+        const int rank = (int)(rest % 2); rest /= 2;
+        const int kc = (int)(rest % nkc);
+        const int slice = (int)(rest / nkc);
+        const int c = (kc * KOCT + oct) * 8 + j;
+        const int ol = row < N ? row : rank * (N / 2) + (row - N);
+        const int lo = row < N ? rank : 0;
+        const int o = slice * NMAX + ol;
+        float v = 0.f;
+        if (c < Cin && o < Cout) v = w[((size_t)o * Cin + c) * 9 + tap] * S;
+        const __half hh = __float2half_rn(v);
+        dst[e] = lo ? __float2half_rn(v - __half2float(hh)) : hh;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -449,9 +726,15 @@ static inline int n_slice(int cout) { return cout <= NMAX ? 1 : (cout + NMAX - 1
 
 using namespace c2m;
 
+static inline size_t layout1_bytes(int Cin, int Cout) { return (size_t)n_slice(Cout) * n_kc(Cin) * 2 * 9 * KOCT * slice_n(Cout) * 16; }
+static inline size_t layout2_bytes(int Cin, int Cout) {
+    const int N = slice_n(Cout);
+    return (size_t)n_slice(Cout) * n_kc(Cin) * 2 * 9 * KOCT * (N + N / 2) * 16;
+}
+
 extern "C" size_t c2m_conv3x3_packed_weight_bytes(int Cin, int Cout) {
     if (Cin <= 0 || Cout <= 0) return 0;
-    return (size_t)W_HDR + (size_t)n_slice(Cout) * n_kc(Cin) * 2 * 9 * KOCT * slice_n(Cout) * 16;
+    return (size_t)W_HDR + layout1_bytes(Cin, Cout) + layout2_bytes(Cin, Cout);       // 1-CTA layout + CTA-pair layout
 }
 
 extern "C" int c2m_conv3x3_pack_weights_f32(const float *w, int Cin, int Cout, void *packed, c2m_stream_t stream) {
@@ -467,6 +750,9 @@ extern "C" int c2m_conv3x3_pack_weights_f32(const float *w, int Cin, int Cout, v
     const int blocks = (int)((total + 255) / 256 > 592 ? 592 : (total + 255) / 256);
     wpack_kernel<<<blocks, 256, 0, st>>>(w, Cin, Cout, N, nkc, ns, reinterpret_cast<uint8_t *>(packed));
     C2M_LAUNCH_CHECK("wpack_kernel");
+    wpack2_kernel<<<blocks, 256, 0, st>>>(w, Cin, Cout, N, nkc, ns, reinterpret_cast<const uint8_t *>(packed),
+                                          reinterpret_cast<__half *>(reinterpret_cast<uint8_t *>(packed) + W_HDR + layout1_bytes(Cin, Cout)));
+    C2M_LAUNCH_CHECK("wpack2_kernel");
     return C2M_OK;
 }
 
@@ -575,11 +861,38 @@ extern "C" int c2m_conv3x3(const c2m_conv3x3_args *a, c2m_stream_t stream) {
     } else {
         m2h = mh; m2l = ml;
     }
-    const size_t smem = (size_t)NBST * 2 * 9 * KOCT * p.N * 16 + NSTAGE * A_STAGE + 4096;
-    C2M_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 0;
     C2M_CUDA(cudaGetDevice(&dev));
     C2M_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    p.w2_off = (unsigned)(W_HDR + layout1_bytes((int)(a->Cin + a->Cin2), a->Cout));
+    bool use2 = true;                                      // CTA pairs (cta_group::2) unless switched off
+    if (const char *ev = getenv("C2M_CONV_2CTA")) use2 = atoi(ev) != 0;
+    if (use2) {
+        const int tiles_img = p.tiles_x * p.tiles_y;
+        p.T = 512 / (2 * p.N) < MAXT ? 512 / (2 * p.N) : MAXT;
+        // small problems: fewer tiles per pair item so that every pair of SMs gets several items
+        while (p.T > 1 && (long long)a->B * ceil_div(tiles_img, 2 * p.T) * p.nslice < 3 * (sms / 2)) p.T /= 2;
+        if (const char *ev = getenv("C2M_CONV_T")) {
+            const int t = atoi(ev);
+            if (t >= 1 && t < p.T) p.T = t;
+        }
+        p.n_st = ceil_div(tiles_img, 2 * p.T);
+        const int n_pair_items = a->B * p.n_st * p.nslice;
+        const int pairs = n_pair_items < sms / 2 ? n_pair_items : sms / 2;
+        const size_t smem2 = (size_t)NBST * 9 * KOCT * (p.N + p.N / 2) * 16 + NSTAGE2 * A_STAGE + 4096;
+        C2M_CUDA(cudaFuncSetAttribute(conv3x3_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        const double cin_t2 = (double)a->Cin + a->Cin2, px2 = (double)a->B * a->H * a->W;
+        const double flops2 = 2.0 * cin_t2 * a->Cout * 9.0 * px2;
+        const double bytes2 = 4.0 * px2 * (cin_t2 + a->Cout * ((a->out_hi ? 1 : 0) + (a->out_f32 ? 1 : 0)) +
+                                           a->Cout * ((a->res_hi ? 1 : 0) + (a->res2_hi ? 1 : 0) + (a->add_f32 ? 1 : 0)));
+        void *ph2 = prof_begin(PROF_CONV3X3, flops2, bytes2, st);
+        conv3x3_umma2_kernel<<<2 * pairs, 384, smem2, st>>>(mh, ml, m2h, m2l, q, p);
+        C2M_LAUNCH_CHECK("conv3x3_umma2_kernel");
+        prof_end(ph2, st);
+        return C2M_OK;
+    }
+    const size_t smem = (size_t)NBST * 2 * 9 * KOCT * p.N * 16 + NSTAGE * A_STAGE + 4096;
+    C2M_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int n_items = a->B * p.n_st * p.nslice;
     // algorithmic work: 2*Cin*Cout*9 flops per output pixel; bytes = PSA in (4 B/elem) + out
     const double cin_t = (double)a->Cin + a->Cin2, px = (double)a->B * a->H * a->W;

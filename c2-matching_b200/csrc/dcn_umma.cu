@@ -63,6 +63,7 @@ struct DcnTc {
     int nstage, nbst;          // ring depths (activation stages, weight chunks); powers of two
     int nstage_shift;          // log2(nstage)
     int tg;                    // pixel tiles per work item (<= T)
+    int policy;                // L2 policies: 1 = input map evict-last, 2 = offsets / mask evict-first, 4 = streaming output stores
     int sc_shift;              // log2(pre_scale) when the flow table is used (idx given, scale in {1,2,4,8}), else -1
     int tab_h, tab_w;          // flow-table cells per tile: 16/s + 2, 8/s + 2
     float inv_ref_gw, inv_scale;   // reciprocals for the exact float-assisted integer divisions
@@ -83,6 +84,11 @@ __device__ __forceinline__ int fast_div(int n, int d, float inv_d) {
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
@@ -283,7 +289,8 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
         const int sg = grp / NS, slot = grp - sg * NS;
         const int P = p.H * p.W, W8 = p.W * 8;
         const int mrow = m / T_C, mcol = m % T_C;
-        const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
+        const uint64_t pol_keep = (d.policy & 1) ? l2_policy_evict_last() : l2_policy_evict_normal();
+        const uint64_t pol_stream = (d.policy & 2) ? l2_policy_evict_first() : l2_policy_evict_normal();
         const int x_img = d.C8 * P * 8;                       // elements per image of one operand half (< 2^31, host-checked)
         const int om_img = (d.om_c8 > 0 ? d.om_c8 * 8 : (d.mask ? 2 : 3) * d.dg * 9) * P;
         const int om_mask_base = 2 * d.dg * 9;
@@ -612,6 +619,13 @@ extern "C" int c2m_dcn_v2_fused_tc(const c2m_dcn_tc_args *a, c2m_stream_t stream
     q.out_hi = reinterpret_cast<__half *>(a->out_hi); q.out_lo = reinterpret_cast<__half *>(a->out_lo);
     q.out_f32 = a->out_f32;
     DcnTc d;
+    d.policy = 7;
+    if (const char *ev = getenv("C2M_DCN_POLICY")) d.policy = atoi(ev);     // tuning experiments
+    p.cs = (d.policy & 4) ? 1 : 0;
+    if (const char *ev = getenv("C2M_L2_PERSIST_MB")) {                      // experiment: L2 set-aside for evict-last lines
+        static int done = 0;
+        if (!done) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)atoi(ev) << 20); done = 1; }
+    }
     d.x_hi = reinterpret_cast<const __half *>(a->x_hi); d.x_lo = reinterpret_cast<const __half *>(a->x_lo);
     d.C8 = a->C / 8;
     d.om_c8 = a->om_octets ? (27 * a->dg + 7) / 8 : 0;

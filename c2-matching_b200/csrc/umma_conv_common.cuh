@@ -19,6 +19,7 @@ struct ConvParams {
     int ps;                   // 0 or 2: PixelShuffle(2) applied to the PSA output
     int stacked;              // 1: accumulator has 2N columns, value = col[c] + col[N + c]
     int dbg;                  // tuning experiments only (C2M_CONV_DBG): 1 = no global stores, 2 = no TMA reloads
+    unsigned w2_off;          // byte offset of the CTA-pair weight layout inside the packed blob
     int cs;                   // 1: PSA output stored with st.global.cs (streaming: the DCN output must not evict the
                               // gathered input map from L2)
     int C8out, Hout, Wout;    // geometry of the PSA output tensor
