@@ -63,7 +63,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
     uint64_t *full = bars, *empty = full + NSTAGE, *bfull = empty + NSTAGE, *bempty = bfull + NBST,
              *tfull = bempty + NBST, *tempty = tfull + MAXT;
     uint32_t *tmem_base_p = reinterpret_cast<uint32_t *>(tempty + MAXT);
-    float *sbias = reinterpret_cast<float *>(tmem_base_p + 2);           // [N]
+    float *sbias = reinterpret_cast<float *>(tmem_base_p + 4);           // [N], 16 B aligned (float4 reads)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_img = p.tiles_x * p.tiles_y;
@@ -167,7 +167,8 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ========================================
-        if (lane == 0) {
+        // the whole warp walks the loop (uniform control flow, operands in uniform registers); one elected lane issues
+        {
             // B = [W_hi | W_lo] stacked along N (2N rows per octet): an N = 64 MMA occupies the tensor
             // pipe as long as an N = 128 one (A-operand fetch bound, ncu: pipe_tc 81 % vs math 40 %),
             // so x_hi*[W_hi|W_lo] (N = 2N) + x_lo*W_hi (N) is 2 MMAs per K step instead of 3
@@ -196,26 +197,28 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                         tc_fence_after();
                         const uint32_t a_hi = smem_u32(sA + stage * A_STAGE);
                         // descriptors of (tap 0, k-step 0); every other MMA is a constant offset away
-                        const uint64_t dah0 = umma_smem_desc(a_hi, A_OCT_B, ROW_B);
-                        const uint64_t dal0 = umma_smem_desc(a_hi + A_HALF, A_OCT_B, ROW_B);
-                        const uint64_t db0 = umma_smem_desc(w_st, b_lbo, 128);
+                        // descriptor words: low = start address (>> 4) | LBO << 16, high = SBO | version (constant)
+                        const uint32_t dah_lo = ((a_hi & 0x3FFFF) >> 4) | ((uint32_t)(A_OCT_B >> 4) << 16);
+                        const uint32_t dal_lo = (((a_hi + A_HALF) & 0x3FFFF) >> 4) | ((uint32_t)(A_OCT_B >> 4) << 16);
+                        const uint32_t da_hi = (uint32_t)(ROW_B >> 4) | (1u << 14);
+                        const uint32_t db_lo0 = ((w_st & 0x3FFFF) >> 4) | ((b_lbo >> 4) << 16);
+                        const uint32_t db_hi = (128u >> 4) | (1u << 14);
 #pragma unroll
                         for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
                             for (int j = 0; j < KOCT / 2; ++j) {
-                                const uint32_t ao = ((tap / 3) * A_C + tap % 3) * 16 + j * 2 * A_OCT_B;
-                                const uint32_t bo = (tap * KOCT + j * 2) * b_lbo;
-                                const uint64_t db = umma_desc_advance(db0, bo);
+                                const uint32_t ao = (((tap / 3) * A_C + tap % 3) * 16 + j * 2 * A_OCT_B) >> 4;
+                                const uint32_t bo = ((tap * KOCT + j * 2) * b_lbo) >> 4;
                                 // x_hi * [W_hi | W_lo]  (N = 2N)  +  x_lo * W_hi  (first N rows only)
-                                umma_f16(d, umma_desc_advance(dah0, ao), db, idesc, (kc | tap | j) != 0);
-                                umma_f16(d, umma_desc_advance(dal0, ao), db, idesc_lo, 1);
+                                umma_f16_w(d, dah_lo + ao, da_hi, db_lo0 + bo, db_hi, idesc, (kc | tap | j) != 0);
+                                umma_f16_w(d, dal_lo + ao, da_hi, db_lo0 + bo, db_hi, idesc_lo, 1);
                             }
                         }
-                        umma_commit(&empty[stage]);
+                        umma_commit_w(&empty[stage]);
                         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-                        if (kc == p.nkc - 1) { umma_commit(&tfull[t]); tph ^= 1u << t; }
+                        if (kc == p.nkc - 1) { umma_commit_w(&tfull[t]); tph ^= 1u << t; }
                     }
-                    if (!w_resident) umma_commit(&bempty[bst]);
+                    if (!w_resident) umma_commit_w(&bempty[bst]);
                     if (++bst == NBST) { bst = 0; bphase ^= 1; }
                 }
                 if (w_resident) { bst = 0; }          // chunk kc always lives in slot kc
@@ -235,6 +238,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
         const float res_scale = ldexpf(1.f, -p.sa_res);
         const float so = ldexpf(1.f, p.sa_out);
         const bool has1 = q.res_hi != nullptr;              // warp-uniform
+        const bool fast = epilogue_fast_ok(q, p);           // specialised straight-line epilogue for full blocks
         uint32_t tph = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             int b, t0, nt, slice;
@@ -254,9 +258,14 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                 tph ^= 1u << t;
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + t * 2 * p.N;
-                if (c0 < p.N)
-                    epilogue_store_block(q, p, taddr, c0, b, y, x, ok, o_base, sbias, out_scale, res_scale, so,
-                                         has1 ? &ra : nullptr);
+                if (c0 < p.N) {
+                    if (fast && c0 + 32 <= p.N && o_base + c0 + 32 <= p.Cout)
+                        epilogue_fast_dispatch<true>(q, p, taddr, c0, b, y, x, ok, o_base, sbias, out_scale, res_scale,
+                                                     has1 ? &ra : nullptr);
+                    else
+                        epilogue_store_block(q, p, taddr, c0, b, y, x, ok, o_base, sbias, out_scale, res_scale, so,
+                                             has1 ? &ra : nullptr);
+                }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[t]);
@@ -303,7 +312,7 @@ conv3x3_umma2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
     uint64_t *full = bars, *empty = full + NSTAGE2, *bfull = empty + NSTAGE2, *bempty = bfull + NBST,
              *tfull = bempty + NBST, *tempty = tfull + MAXT;
     uint32_t *tmem_base_p = reinterpret_cast<uint32_t *>(tempty + MAXT);
-    float *sbias = reinterpret_cast<float *>(tmem_base_p + 2);           // [N]
+    float *sbias = reinterpret_cast<float *>(tmem_base_p + 4);           // [N], 16 B aligned (float4 reads)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -399,11 +408,17 @@ conv3x3_umma2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && leader) {
+        if (leader) {
             // ================================ MMA issuer (leader CTA) ==========================
+            // whole warp, uniform control flow; one elected lane issues (see umma_f16_w).
+            // Two tiles are in flight at once and their MMAs alternate: consecutive MMAs into the SAME accumulator
+            // serialise on the accumulate dependency (ncu: tensor pipe 57 % active with 64-cycle MMAs, shared-memory
+            // banks 34 %, issue slots idle), so the instruction stream interleaves two independent accumulators.
             const uint32_t idesc = umma_idesc_f16(256, 2 * p.N, 0);
             const uint32_t idesc_lo = umma_idesc_f16(256, p.N, 0);
             const uint32_t b_lbo = w_rows * 16;              // next channel octet of the weights
+            const uint32_t da_hi = (uint32_t)(ROW_B >> 4) | (1u << 14);
+            const uint32_t db_hi = (128u >> 4) | (1u << 14);
             int stage = 0, phase = 0, bst = 0, bphase = 0;
             uint32_t tph = 0;
             for (int item = pair; item < n_items; item += n_pairs) {
@@ -416,34 +431,63 @@ conv3x3_umma2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
                         tc_fence_after();
                     }
                     const uint32_t w_st = smem_u32(sW + bst * w_chunk);
-                    for (int t = 0; t < nt; ++t) {
+                    const uint32_t db_lo0 = ((w_st & 0x3FFFF) >> 4) | ((b_lbo >> 4) << 16);              // rows [0, N): MMA 1
+                    const uint32_t db_lo1 = (((w_st + p.N * 16) & 0x3FFFF) >> 4) | ((b_lbo >> 4) << 16);   // rows [N, 1.5 N): MMA 2
+                    for (int t = 0; t < nt; t += 2) {
+                        const bool two = t + 1 < nt;
+                        int stage1 = stage + 1, phase1 = phase;
+                        if (stage1 == NSTAGE2) { stage1 = 0; phase1 ^= 1; }
                         if (kc == 0) {
                             mbar_wait(&tempty[t], ((tph >> t) & 1u) ^ 1u);
+                            if (two) mbar_wait(&tempty[t + 1], ((tph >> (t + 1)) & 1u) ^ 1u);
                             tc_fence_after();
                         }
-                        const uint32_t d = tmem_base + t * 2 * p.N;
+                        const uint32_t d0 = tmem_base + t * 2 * p.N, d1 = d0 + 2 * p.N;
                         mbar_wait(&full[stage], phase);
+                        if (two) mbar_wait(&full[stage1], phase1);
                         tc_fence_after();
-                        const uint32_t a_hi = smem_u32(sA + stage * A_STAGE);
-                        const uint64_t dah0 = umma_smem_desc(a_hi, A_OCT_B, ROW_B);
-                        const uint64_t dal0 = umma_smem_desc(a_hi + A_HALF, A_OCT_B, ROW_B);
-                        const uint64_t db0 = umma_smem_desc(w_st, b_lbo, 128);               // rows [0, N): MMA 1
-                        const uint64_t db1 = umma_smem_desc(w_st + p.N * 16, b_lbo, 128);    // rows [N, 1.5 N): MMA 2
+                        const uint32_t a0 = smem_u32(sA + stage * A_STAGE), a1 = smem_u32(sA + stage1 * A_STAGE);
+                        const uint32_t ah0 = ((a0 & 0x3FFFF) >> 4) | ((uint32_t)(A_OCT_B >> 4) << 16);
+                        const uint32_t al0 = (((a0 + A_HALF) & 0x3FFFF) >> 4) | ((uint32_t)(A_OCT_B >> 4) << 16);
+                        const uint32_t ah1 = ((a1 & 0x3FFFF) >> 4) | ((uint32_t)(A_OCT_B >> 4) << 16);
+                        const uint32_t al1 = (((a1 + A_HALF) & 0x3FFFF) >> 4) | ((uint32_t)(A_OCT_B >> 4) << 16);
+                        if (two) {
 #pragma unroll
-                        for (int tap = 0; tap < 9; ++tap) {
+                            for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
-                            for (int j = 0; j < KOCT / 2; ++j) {
-                                const uint32_t ao = ((tap / 3) * A_C + tap % 3) * 16 + j * 2 * A_OCT_B;
-                                const uint32_t bo = (tap * KOCT + j * 2) * b_lbo;
-                                umma2_f16(d, umma_desc_advance(dah0, ao), umma_desc_advance(db0, bo), idesc, (kc | tap | j) != 0);
-                                umma2_f16(d, umma_desc_advance(dal0, ao), umma_desc_advance(db1, bo), idesc_lo, 1);
+                                for (int j = 0; j < KOCT / 2; ++j) {
+                                    const uint32_t ao = (((tap / 3) * A_C + tap % 3) * 16 + j * 2 * A_OCT_B) >> 4;
+                                    const uint32_t bo = ((tap * KOCT + j * 2) * b_lbo) >> 4;
+                                    const uint32_t acc = (kc | tap | j) != 0;
+                                    umma2_f16_w(d0, ah0 + ao, da_hi, db_lo0 + bo, db_hi, idesc, acc);
+                                    umma2_f16_w(d1, ah1 + ao, da_hi, db_lo0 + bo, db_hi, idesc, acc);
+                                    umma2_f16_w(d0, al0 + ao, da_hi, db_lo1 + bo, db_hi, idesc_lo, 1);
+                                    umma2_f16_w(d1, al1 + ao, da_hi, db_lo1 + bo, db_hi, idesc_lo, 1);
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+                                for (int j = 0; j < KOCT / 2; ++j) {
+                                    const uint32_t ao = (((tap / 3) * A_C + tap % 3) * 16 + j * 2 * A_OCT_B) >> 4;
+                                    const uint32_t bo = ((tap * KOCT + j * 2) * b_lbo) >> 4;
+                                    umma2_f16_w(d0, ah0 + ao, da_hi, db_lo0 + bo, db_hi, idesc, (kc | tap | j) != 0);
+                                    umma2_f16_w(d0, al0 + ao, da_hi, db_lo1 + bo, db_hi, idesc_lo, 1);
+                                }
                             }
                         }
-                        umma_commit2(&empty[stage]);
+                        umma_commit2_w(&empty[stage]);
+                        if (two) umma_commit2_w(&empty[stage1]);
+                        if (kc == p.nkc - 1) {
+                            umma_commit2_w(&tfull[t]);
+                            tph ^= 1u << t;
+                            if (two) { umma_commit2_w(&tfull[t + 1]); tph ^= 1u << (t + 1); }
+                        }
+                        if (two) { stage = stage1; phase = phase1; }
                         if (++stage == NSTAGE2) { stage = 0; phase ^= 1; }
-                        if (kc == p.nkc - 1) { umma_commit2(&tfull[t]); tph ^= 1u << t; }
                     }
-                    if (!w_resident) umma_commit2(&bempty[bst]);
+                    if (!w_resident) umma_commit2_w(&bempty[bst]);
                     if (++bst == NBST) { bst = 0; bphase ^= 1; }
                 }
                 if (w_resident) { bst = 0; }
@@ -482,6 +526,7 @@ conv3x3_umma2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
         const float res_scale = ldexpf(1.f, -p.sa_res);
         const float so = ldexpf(1.f, p.sa_out);
         const bool has1 = q.res_hi != nullptr;              // warp-uniform
+        const bool fast = epilogue_fast_ok(q, p);           // specialised straight-line epilogue for full blocks
         uint32_t tph = 0;
         for (int item = pair; item < n_items; item += n_pairs) {
             int b, t0, nt, slice;
@@ -501,9 +546,14 @@ conv3x3_umma2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
                 tph ^= 1u << t;
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + t * 2 * p.N;
-                if (c0 < p.N)
-                    epilogue_store_block(q, p, taddr, c0, b, y, x, ok, o_base, sbias, out_scale, res_scale, so,
-                                         has1 ? &ra : nullptr);
+                if (c0 < p.N) {
+                    if (fast && c0 + 32 <= p.N && o_base + c0 + 32 <= p.Cout)
+                        epilogue_fast_dispatch<true>(q, p, taddr, c0, b, y, x, ok, o_base, sbias, out_scale, res_scale,
+                                                     has1 ? &ra : nullptr);
+                    else
+                        epilogue_store_block(q, p, taddr, c0, b, y, x, ok, o_base, sbias, out_scale, res_scale, so,
+                                             has1 ? &ra : nullptr);
+                }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {

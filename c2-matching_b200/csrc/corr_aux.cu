@@ -446,26 +446,51 @@ __global__ void __launch_bounds__(256) rescore_kernel(const float *__restrict__ 
 
 // Exhaustive exact re-scan of the flagged (query, chunk) pairs.  Each list entry is cut into OVF_SPLIT slices of
 // the flagged chunks' Ref patches; a block takes (entry, slice) work items grid-stride, its warps stride over the
-// slice, and the result is merged into `best` with a 64-bit atomicMax on the packed (score, index) key.  With top-4
-// lists this runs for a handful of queries per batch on real data (four candidates within ~1e-4 of each other in
-// one chunk, or exact ties), but it is what makes the candidate lists sufficient instead of "empirically enough".
+// slice, and the result is merged into `best` with a 64-bit atomicMax on the packed (score, index) key.
+// Per Ref patch a warp first forms the fp32 FMA score (query patch cached in shared memory, ~110 instructions); only
+// patches whose fp32 score reaches  (best exact score so far) - E32,  E32 = (K + 8) * 2^-24 * ||P_q|| * ||P_r|| * rinv_r
+// (the worst-case error of a K-term fp32 FMA chain), can still win and get the exact evaluation (~1300 instructions:
+// an IEEE division per element).  With top-4 lists fed by the two best of every 28-patch block this runs for a few
+// queries per batch, but it is what makes the candidate lists sufficient instead of "empirically enough".
 constexpr int OVF_SPLIT = 64;
 
 __global__ void __launch_bounds__(256) rescore_overflow_kernel(const float *__restrict__ pin, const float *__restrict__ pref,
-                                                               CorrGeom g, CorrChunkGeom cg, int nchunk, int is_norm,
+                                                               const float *__restrict__ rinv, CorrGeom g, CorrChunkGeom cg,
+                                                               int nchunk, int is_norm, float e32_coef,
+                                                               const unsigned *__restrict__ max_pn_bits,
+                                                               const float *__restrict__ qnorm, int qs_floats,
                                                                const CorrOverflow *__restrict__ ovf,
                                                                const unsigned *__restrict__ ovf_count,
                                                                unsigned long long *__restrict__ best_out) {
+    extern __shared__ __align__(16) float qs[];          // query patch [taps][Cp] (qs_floats == 0: no prefilter)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned count = *ovf_count;
     const int per_tile = cg.tile_rows * cg.tile_cols;
+    const int taps = g.patch * g.patch;
     for (unsigned wi = blockIdx.x; wi < count * OVF_SPLIT; wi += gridDim.x) {
         const CorrOverflow o = ovf[wi / OVF_SPLIT];
         const int part_i = wi % OVF_SPLIT;
         const int b = o.query / g.NQ, q = o.query - b * g.NQ;
         const float *pinb = pin + (size_t)b * g.h * g.w * g.Cp;
         const float *prefb = pref + (size_t)b * g.hr * g.wr * g.Cp;
+        const float *rinvb = rinv + (size_t)b * g.NR;
         const int qp = ((q / g.gw) * g.s_in) * g.w + (q % g.gw) * g.s_in;
+        if (qs_floats) {
+            __syncthreads();                               // previous work item's readers are done
+            for (int i = threadIdx.x * 4; i < taps * g.Cp; i += 1024) {
+                const int tap = i / g.Cp, c = i - tap * g.Cp;
+                *reinterpret_cast<float4 *>(qs + i) =
+                    *reinterpret_cast<const float4 *>(pinb + (size_t)(qp + (tap / g.patch) * g.w + tap % g.patch) * g.Cp + c);
+            }
+            __syncthreads();
+        }
+        float sstar = -INFINITY;                           // exact lower bound on the winner's score
+        {
+            const unsigned long long k0 = best_out[o.query];
+            int r0;
+            if (k0 != 0ull) best_unkey(k0, sstar, r0);
+        }
+        const float e32 = e32_coef * qnorm[o.query] * (is_norm ? 1.f : __uint_as_float(*max_pn_bits)) + 1e-6f;
         float best = -INFINITY;
         int besti = 0x7fffffff;
         for (int c = 0; c < nchunk; ++c) {
@@ -486,6 +511,25 @@ __global__ void __launch_bounds__(256) rescore_overflow_kernel(const float *__re
                     r = ry * g.rw + rx;
                 }
                 const int rp = ((r / g.rw) * g.s_ref) * g.wr + (r % g.rw) * g.s_ref;
+                if (qs_floats) {
+                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 3
+                    for (int tap = 0; tap < taps; ++tap) {
+                        const float *rrow = prefb + (size_t)(rp + (tap / g.patch) * g.wr + tap % g.patch) * g.Cp;
+#pragma unroll 2
+                        for (int cc = lane * 4; cc < g.Cp; cc += 128) {
+                            const float4 rv = *reinterpret_cast<const float4 *>(rrow + cc);
+                            const float4 qv = *reinterpret_cast<const float4 *>(qs + tap * g.Cp + cc);
+                            a0 = fmaf(qv.x, rv.x, a0); a1 = fmaf(qv.y, rv.y, a1);
+                            a2 = fmaf(qv.z, rv.z, a2); a3 = fmaf(qv.w, rv.w, a3);
+                        }
+                    }
+                    float s32 = (a0 + a1) + (a2 + a3);
+#pragma unroll
+                    for (int of = 16; of; of >>= 1) s32 += __shfl_xor_sync(0xffffffffu, s32, of);
+                    s32 *= rinvb[r];
+                    if (s32 < fmaxf(sstar, best) - e32) continue;        // cannot beat the best exact score (warp-uniform)
+                }
                 const float s = exact_score_warp(pinb, prefb, g, qp, rp, is_norm, lane);
                 if (cand_better(s, r, best, besti)) { best = s; besti = r; }
             }
@@ -514,8 +558,12 @@ int corr_rescore_launch(const CorrGeom &g, const CorrWorkspace &ws, const CorrCh
     rescore_kernel<<<grid, 256, 0, st>>>(ws.p32_in, ws.p32_ref, ws.part, g, ws.nchunk, window_coef, ws.max_pn_bits,
                                          is_norm, ws.best, ws.qnorm, ws.ovf, ws.ovf_count);
     C2M_LAUNCH_CHECK("rescore_kernel");
-    rescore_overflow_kernel<<<592, 256, 0, st>>>(ws.p32_in, ws.p32_ref, g, cg, ws.nchunk, is_norm, ws.ovf, ws.ovf_count,
-                                                 ws.best);
+    // fp32 prefilter of the re-scan: query patch in shared memory when it fits (it does for every model shape)
+    const int K = g.Cp * g.patch * g.patch;
+    const int qs_floats = K * 4 <= 48 * 1024 ? K : 0;
+    const float e32_coef = ldexpf(1.f, -24) * (float)(K + 8);
+    rescore_overflow_kernel<<<592, 256, qs_floats * 4, st>>>(ws.p32_in, ws.p32_ref, ws.rinv, g, cg, ws.nchunk, is_norm, e32_coef,
+                                                             ws.max_pn_bits, ws.qnorm, qs_floats, ws.ovf, ws.ovf_count, ws.best);
     C2M_LAUNCH_CHECK("rescore_overflow_kernel");
     const int n = g.B * g.NQ;
     rescore_finish_kernel<<<ceil_div(n, 256), 256, 0, st>>>(ws.best, ws.qnorm, n, norm_input, idx, val);

@@ -170,8 +170,8 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap tm_in_hi, const __grid_cons
         // ================================ epilogue =========================================
         // Branch-free inner loop (the per-score compare-and-insert of the first version kept the tensor pipe at
         // 38 %): per 32-column block (two Ref block rows, 28 valid scores) only min / max run per score —
-        // m1 = block best, m2 = block second best — and just the block winner is offered to the top-4 list.
-        // Everything that is not in the list (block runners-up, evicted entries) feeds `dropped`, the largest score
+        // m1 >= m2 >= m3 = the block's three best — and only m1, m2 are offered to the top-4 list.
+        // Everything that is not in the list (block thirds, evicted entries) feeds `dropped`, the largest score
         // left behind; the rescoring pass re-scans the chunk exhaustively when `dropped` reaches its window.
         const int e = threadIdx.x - 128;                    // 0..127 = accumulator row m = 16 * block row + block column
         const int quarter = warp & 3;
@@ -209,7 +209,7 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap tm_in_hi, const __grid_cons
                     tmem_ld_32x32(taddr + cc * 32, reg);
                     tmem_ld_wait();
                     float sv[2 * TV];
-                    float m1 = -INFINITY, m2 = -INFINITY;
+                    float m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;      // block best, second, third
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
 #pragma unroll
@@ -222,18 +222,27 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap tm_in_hi, const __grid_cons
                             asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(cx), "=f"(cy) : "r"(rc_s + (cc * 32 + j) * 8));
                             const float sc = fmaf((__uint_as_float(reg[j]) + t1) + t2, cx, cy);
                             sv[hh * TV + v] = sc;
+                            m3 = fmaxf(m3, fminf(m2, sc));
                             m2 = fmaxf(m2, fminf(m1, sc));
                             m1 = fmaxf(m1, sc);
                         }
                     }
-                    dropped = fmaxf(dropped, m2);
+                    // the block's two best are offered to the list (neighbouring Ref patches overlap in 6 of 9 pixels,
+                    // so the runner-up next to a good match is the likeliest near-tie); the third best is left behind
+                    dropped = fmaxf(dropped, m3);
                     if (m1 > cv[3]) {                        // rare once the list has warmed up
-                        int jw = 0;
+                        int k1 = 0, k2 = 0;
 #pragma unroll
                         for (int k = 2 * TV - 1; k >= 0; --k)
-                            if (sv[k] == m1) jw = (k / TV) * 16 + k % TV;         // lowest column among equals
-                        const int r = (ry0 + cc * 2 + (jw >> 4)) * p.rw + rx0 + (jw & 15);
-                        cand_push(m1, r, cv, ci, dropped);
+                            if (sv[k] == m1) k1 = k;                              // lowest column among equals
+#pragma unroll
+                        for (int k = 2 * TV - 1; k >= 0; --k)
+                            if (sv[k] == m2 && k != k1) k2 = k;
+                        const int rb = (ry0 + cc * 2) * p.rw + rx0;
+                        cand_push(m1, rb + (k1 / TV) * p.rw + k1 % TV, cv, ci, dropped);
+                        cand_push(m2, rb + (k2 / TV) * p.rw + k2 % TV, cv, ci, dropped);
+                    } else {
+                        dropped = fmaxf(dropped, m2);
                     }
                 }
                 tc_fence_before();

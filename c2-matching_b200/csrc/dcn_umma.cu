@@ -192,7 +192,7 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ========================================
-        if (lane == 0) {
+        {   // whole warp, uniform control flow; one elected lane issues (see umma_f16_w)
             const uint32_t idesc = umma_idesc_f16(128, p.N, 0);
             const uint32_t b_lbo = p.N * 16;
             int stage = 0, phase = 0, bst = 0, bphase = 0;
@@ -223,15 +223,15 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
                             const uint64_t dal = umma_smem_desc(a_lo + ao, A_OCT_B, 128);
                             const uint64_t dbh = umma_smem_desc(w_hi + bo, b_lbo, 128);
                             const uint64_t dbl = umma_smem_desc(w_lo + bo, b_lbo, 128);
-                            umma_f16(dacc, dah, dbh, idesc, (kc | j) != 0);
-                            umma_f16(dacc, dah, dbl, idesc, 1);
-                            umma_f16(dacc, dal, dbh, idesc, 1);
+                            umma_f16_w(dacc, dah, dbh, idesc, (kc | j) != 0);
+                            umma_f16_w(dacc, dah, dbl, idesc, 1);
+                            umma_f16_w(dacc, dal, dbh, idesc, 1);
                         }
-                        umma_commit(&empty[stage]);
+                        umma_commit_w(&empty[stage]);
                         if (++stage == d.nstage) { stage = 0; phase ^= 1; }
-                        if (kc == p.nkc - 1) { umma_commit(&tfull[a]); tph ^= 1u << a; }
+                        if (kc == p.nkc - 1) { umma_commit_w(&tfull[a]); tph ^= 1u << a; }
                     }
-                    umma_commit(&bempty[bst]);
+                    umma_commit_w(&bempty[bst]);
                     if (++bst == d.nbst) { bst = 0; bphase ^= 1; }
                 }
                 abase += nt;
@@ -247,6 +247,7 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
         const float out_scale = ldexpf(1.f, -(p.sa_in + sw));
         const float res_scale = 1.f;
         const float so = ldexpf(1.f, p.sa_out);
+        const bool fast = epilogue_fast_ok(q, p);
         uint32_t tph = 0;
         int abase = 0;
         for (int i = e; i < p.N; i += 128) sbias[i] = (q.bias && i < p.Cout) ? q.bias[i] : 0.f;
@@ -266,8 +267,12 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
                 tph ^= 1u << a;
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * p.N;
-                for (int c0 = 0; c0 < p.N; c0 += 32)
-                    epilogue_store_block(q, p, taddr, c0, b, y, x, ok, o_base, sbias, out_scale, res_scale, so);
+                for (int c0 = 0; c0 < p.N; c0 += 32) {
+                    if (fast && c0 + 32 <= p.N && c0 + 32 <= p.Cout)
+                        epilogue_fast_dispatch<false>(q, p, taddr, c0, b, y, x, ok, o_base, sbias, out_scale, res_scale, nullptr);
+                    else
+                        epilogue_store_block(q, p, taddr, c0, b, y, x, ok, o_base, sbias, out_scale, res_scale, so);
+                }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[a]);

@@ -218,4 +218,109 @@ __device__ __forceinline__ void epilogue_store_block(const ConvPtrs &q, const Co
                     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Specialised epilogue of one full 32-column block (4 complete channel octets): the generic function above spends
+// ~930 SASS instructions per (warp, tile) on per-element bounds predicates, activation selects and address
+// arithmetic — with it the 8 epilogue warps were busy 87 % of the time while the tensor pipe sat at 57 % (ncu,
+// profiles/r02_conv_epilogue_bound.md).  Here everything that is uniform per launch is a template parameter and the
+// block is straight-line code: ~10 instructions per output element.
+//   ACT 0 none / 1 ReLU / 2 LeakyReLU(0.1);  RES: one PSA residual (prefetched);  F32OCT: octet-planar fp32 output
+//   instead of PSA;  STACKED: accumulator columns [c, N + c) hold the x*W_hi and x*W_lo partial sums.
+// Preconditions (checked by the caller, warp-uniform): c0 + 32 <= N, o_base + c0 + 32 <= Cout, ps == 0, no res2,
+// sa_out == 0, exactly one output kind.
+// ---------------------------------------------------------------------------------------------------------------
+template <int ACT, bool RES, bool F32OCT, bool STACKED>
+__device__ __forceinline__ void epilogue_fast_block(const ConvPtrs &q, const ConvParams &p, uint32_t taddr, int c0, int b,
+                                                    int y, int x, bool ok, int o_base, const float *sbias,
+                                                    float out_scale, float res_scale, const ResRegs *r1) {
+    uint32_t reg[32];
+    tmem_ld_32x32(taddr + c0, reg);
+    if (STACKED) {
+        uint32_t reg2[32];
+        tmem_ld_32x32(taddr + p.N + c0, reg2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) reg[j] = __float_as_uint(__uint_as_float(reg[j]) + __uint_as_float(reg2[j]));
+    } else {
+        tmem_ld_wait();
+    }
+    if (!ok) return;
+    const size_t plane = (size_t)p.H * p.W * 8;                       // elements per channel octet
+    const size_t off0 = ((size_t)b * p.C8out + (o_base + c0) / 8) * plane + ((size_t)y * p.W + x) * 8;
+#pragma unroll
+    for (int o8 = 0; o8 < 4; ++o8) {
+        const float4 b0 = *reinterpret_cast<const float4 *>(sbias + c0 + o8 * 8);
+        const float4 b1 = *reinterpret_cast<const float4 *>(sbias + c0 + o8 * 8 + 4);
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float a = fmaf(__uint_as_float(reg[o8 * 8 + j]), out_scale, bb[j]);
+            if (ACT == 1) a = fmaxf(a, 0.f);
+            else if (ACT == 2) a = fmaxf(a, 0.1f * a);                  // LeakyReLU(0.1): max(a, 0.1 a)
+            v[j] = a;
+        }
+        if (RES) {
+            const __half2 *hh = reinterpret_cast<const __half2 *>(&r1->h[o8]);
+            const __half2 *ll = reinterpret_cast<const __half2 *>(&r1->l[o8]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 fh = __half22float2(hh[j]), fl = __half22float2(ll[j]);
+                v[2 * j] = fmaf(fh.x + fl.x, res_scale, v[2 * j]);
+                v[2 * j + 1] = fmaf(fh.y + fl.y, res_scale, v[2 * j + 1]);
+            }
+        }
+        const size_t off = off0 + o8 * plane;
+        if (F32OCT) {
+            float4 *dst = reinterpret_cast<float4 *>(q.out_f32 + off);
+            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+        } else {
+            __align__(16) __half2 h4[4];
+            __align__(16) __half2 l4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const __half2 hq = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+                const float2 hf = __half22float2(hq);
+                h4[j] = hq;
+                l4[j] = __floats2half2_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
+            }
+            if (p.cs) {
+                __stcs(reinterpret_cast<uint4 *>(q.out_hi + off), *reinterpret_cast<const uint4 *>(h4));
+                __stcs(reinterpret_cast<uint4 *>(q.out_lo + off), *reinterpret_cast<const uint4 *>(l4));
+            } else {
+                *reinterpret_cast<uint4 *>(q.out_hi + off) = *reinterpret_cast<const uint4 *>(h4);
+                *reinterpret_cast<uint4 *>(q.out_lo + off) = *reinterpret_cast<const uint4 *>(l4);
+            }
+        }
+    }
+}
+
+// warp-uniform: can this launch's full blocks take the specialised epilogue?
+__device__ __forceinline__ bool epilogue_fast_ok(const ConvPtrs &q, const ConvParams &p) {
+    const bool psa_only = q.out_hi && !q.out_f32;
+    const bool oct_only = q.out_f32 && p.f32_mode == 2 && !q.out_hi;
+    return p.ps == 0 && !q.res2_hi && p.sa_out == 0 && !(p.dbg & 1) && (psa_only || (oct_only && !q.res_hi));
+}
+
+template <bool STACKED>
+__device__ __forceinline__ void epilogue_fast_dispatch(const ConvPtrs &q, const ConvParams &p, uint32_t taddr, int c0, int b,
+                                                       int y, int x, bool ok, int o_base, const float *sbias,
+                                                       float out_scale, float res_scale, const ResRegs *r1) {
+    const bool oct = q.out_f32 != nullptr;
+    if (oct) {
+        if (p.act == 0) epilogue_fast_block<0, false, true, STACKED>(q, p, taddr, c0, b, y, x, ok, o_base, sbias, out_scale, res_scale, r1);
+        else if (p.act == 1) epilogue_fast_block<1, false, true, STACKED>(q, p, taddr, c0, b, y, x, ok, o_base, sbias, out_scale, res_scale, r1);
+        else epilogue_fast_block<2, false, true, STACKED>(q, p, taddr, c0, b, y, x, ok, o_base, sbias, out_scale, res_scale, r1);
+    } else if (r1) {
+        if (p.act == 0) epilogue_fast_block<0, true, false, STACKED>(q, p, taddr, c0, b, y, x, ok, o_base, sbias, out_scale, res_scale, r1);
+        else if (p.act == 1) epilogue_fast_block<1, true, false, STACKED>(q, p, taddr, c0, b, y, x, ok, o_base, sbias, out_scale, res_scale, r1);
+        else epilogue_fast_block<2, true, false, STACKED>(q, p, taddr, c0, b, y, x, ok, o_base, sbias, out_scale, res_scale, r1);
+    } else {
+        if (p.act == 0) epilogue_fast_block<0, false, false, STACKED>(q, p, taddr, c0, b, y, x, ok, o_base, sbias, out_scale, res_scale, r1);
+        else if (p.act == 1) epilogue_fast_block<1, false, false, STACKED>(q, p, taddr, c0, b, y, x, ok, o_base, sbias, out_scale, res_scale, r1);
+        else epilogue_fast_block<2, false, false, STACKED>(q, p, taddr, c0, b, y, x, ok, o_base, sbias, out_scale, res_scale, r1);
+    }
+}
+
 }  // namespace c2m
