@@ -248,18 +248,40 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
             if (threadIdx.x - 128 < p.N) sbias[threadIdx.x - 128] =
                 (q.bias && o_base + (int)threadIdx.x - 128 < p.Cout) ? q.bias[o_base + threadIdx.x - 128] : 0.f;
             asm volatile("bar.sync 1, 256;" ::: "memory");
+            const bool full_blk = fast && c0 + 32 <= p.N && o_base + c0 + 32 <= p.Cout;
             for (int t = 0; t < nt; ++t) {
                 const int tt = t0 + t;
                 const int y = (tt / p.tiles_x) * T_R + e / T_C, x = (tt % p.tiles_x) * T_C + e % T_C;
                 const bool ok = y < p.H && x < p.W;
                 ResRegs ra;
-                if (has1 && c0 < p.N) prefetch_residual(q.res_hi, q.res_lo, p, b, y, x, ok, o_base, c0, ra);
+                if (has1 && c0 < p.N) {
+                    if (full_blk) {
+                        prefetch_residual_full(q.res_hi, q.res_lo, p, b, y, x, ok, o_base, c0, ra);
+                        // next tile's residual octets -> L2 now, so that its register prefetch (issued just before its
+                        // accumulator wait, which is short since the epilogue got lean) finds them on chip
+                        if (t + 1 < nt) {
+                            const int tn = tt + 1;
+                            const int yn = (tn / p.tiles_x) * T_R + e / T_C, xn = (tn % p.tiles_x) * T_C + e % T_C;
+                            if (yn < p.H && xn < p.W) {
+                                const size_t plane = (size_t)p.H * p.W * 8;
+                                const size_t off = ((size_t)b * p.C8out + (o_base + c0) / 8) * plane + ((size_t)yn * p.W + xn) * 8;
+#pragma unroll
+                                for (int o8 = 0; o8 < 4; ++o8) {
+                                    asm volatile("prefetch.global.L2 [%0];" ::"l"(q.res_hi + off + o8 * plane));
+                                    asm volatile("prefetch.global.L2 [%0];" ::"l"(q.res_lo + off + o8 * plane));
+                                }
+                            }
+                        }
+                    } else {
+                        prefetch_residual(q.res_hi, q.res_lo, p, b, y, x, ok, o_base, c0, ra);
+                    }
+                }
                 mbar_wait(&tfull[t], (tph >> t) & 1u);
                 tph ^= 1u << t;
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + t * 2 * p.N;
                 if (c0 < p.N) {
-                    if (fast && c0 + 32 <= p.N && o_base + c0 + 32 <= p.Cout)
+                    if (full_blk)
                         epilogue_fast_dispatch<true>(q, p, taddr, c0, b, y, x, ok, o_base, sbias, out_scale, res_scale,
                                                      has1 ? &ra : nullptr);
                     else
@@ -541,7 +563,12 @@ conv3x3_umma2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
                 const int y = (tt / p.tiles_x) * T_R + e / T_C, x = (tt % p.tiles_x) * T_C + e % T_C;
                 const bool ok = tt < tiles_img && y < p.H && x < p.W;
                 ResRegs ra;
-                if (has1 && c0 < p.N) prefetch_residual(q.res_hi, q.res_lo, p, b, y, x, ok, o_base, c0, ra);
+                if (has1 && c0 < p.N) {
+                    if (fast && c0 + 32 <= p.N && o_base + c0 + 32 <= p.Cout)
+                        prefetch_residual_full(q.res_hi, q.res_lo, p, b, y, x, ok, o_base, c0, ra);
+                    else
+                        prefetch_residual(q.res_hi, q.res_lo, p, b, y, x, ok, o_base, c0, ra);
+                }
                 mbar_wait(&tfull[t], (tph >> t) & 1u);
                 tph ^= 1u << t;
                 tc_fence_after();
@@ -915,7 +942,10 @@ extern "C" int c2m_conv3x3(const c2m_conv3x3_args *a, c2m_stream_t stream) {
     C2M_CUDA(cudaGetDevice(&dev));
     C2M_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     p.w2_off = (unsigned)(W_HDR + layout1_bytes((int)(a->Cin + a->Cin2), a->Cout));
-    bool use2 = true;                                      // CTA pairs (cta_group::2) unless switched off
+    // CTA pairs (cta_group::2): implemented and parity-tested, but measured SLOWER than the 1-CTA kernel on every
+    // shape of the network (profiles/r02_conv_epilogue_bound.md: the kernel was epilogue-bound, not operand-fetch
+    // bound) — off by default, C2M_CONV_2CTA=1 selects it for experiments.
+    bool use2 = false;
     if (const char *ev = getenv("C2M_CONV_2CTA")) use2 = atoi(ev) != 0;
     if (use2) {
         const int tiles_img = p.tiles_x * p.tiles_y;

@@ -229,10 +229,41 @@ __device__ __forceinline__ void epilogue_store_block(const ConvPtrs &q, const Co
 // Preconditions (checked by the caller, warp-uniform): c0 + 32 <= N, o_base + c0 + 32 <= Cout, ps == 0, no res2,
 // sa_out == 0, exactly one output kind.
 // ---------------------------------------------------------------------------------------------------------------
+// Branch-free residual prefetch of a FULL 32-column block (all four octets exist): the loads land directly in their
+// final registers.  (The generic prefetch_residual guards every octet with a branch; ptxas then copies each loaded
+// value inside its basic block, i.e. waits for one load round trip per octet.)
+__device__ __forceinline__ void prefetch_residual_full(const __half *rh, const __half *rl, const ConvParams &p, int b, int y,
+                                                       int x, bool ok, int o_base, int c0, ResRegs &r) {
+    const size_t plane = (size_t)p.H * p.W * 8;
+    const size_t off0 = ((size_t)b * p.C8out + (o_base + c0) / 8) * plane + (ok ? ((size_t)y * p.W + x) * 8 : (size_t)0);
+#pragma unroll
+    for (int o8 = 0; o8 < 4; ++o8) {
+        r.h[o8] = __ldg(reinterpret_cast<const uint4 *>(rh + off0 + o8 * plane));
+        r.l[o8] = __ldg(reinterpret_cast<const uint4 *>(rl + off0 + o8 * plane));
+    }
+}
+
+// The residual octets are fetched BEFORE the thread blocks on the accumulator so their HBM / L2 latency overlaps the
+// MMAs.  Their fp16 -> fp32 conversion does not depend on the accumulator, so the compiler hoists it above the wait —
+// which puts four serialised load round trips in front of every tile (measured: +160 us on a 64->64 @640x640 launch).
+// This no-op "modifies" the registers after the wait, so nothing can consume them earlier.
+__device__ __forceinline__ void pin_residual(ResRegs &r) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        asm volatile("" : "+r"(r.h[i].x), "+r"(r.h[i].y), "+r"(r.h[i].z), "+r"(r.h[i].w));
+        asm volatile("" : "+r"(r.l[i].x), "+r"(r.l[i].y), "+r"(r.l[i].z), "+r"(r.l[i].w));
+    }
+}
+__device__ __forceinline__ float4 lds_f4(const float *p) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+    return v;
+}
+
 template <int ACT, bool RES, bool F32OCT, bool STACKED>
 __device__ __forceinline__ void epilogue_fast_block(const ConvPtrs &q, const ConvParams &p, uint32_t taddr, int c0, int b,
                                                     int y, int x, bool ok, int o_base, const float *sbias,
-                                                    float out_scale, float res_scale, const ResRegs *r1) {
+                                                    float out_scale, float res_scale, ResRegs *r1) {
     uint32_t reg[32];
     tmem_ld_32x32(taddr + c0, reg);
     if (STACKED) {
@@ -244,13 +275,13 @@ __device__ __forceinline__ void epilogue_fast_block(const ConvPtrs &q, const Con
     } else {
         tmem_ld_wait();
     }
+    if (RES) pin_residual(*r1);
     if (!ok) return;
     const size_t plane = (size_t)p.H * p.W * 8;                       // elements per channel octet
     const size_t off0 = ((size_t)b * p.C8out + (o_base + c0) / 8) * plane + ((size_t)y * p.W + x) * 8;
 #pragma unroll
     for (int o8 = 0; o8 < 4; ++o8) {
-        const float4 b0 = *reinterpret_cast<const float4 *>(sbias + c0 + o8 * 8);
-        const float4 b1 = *reinterpret_cast<const float4 *>(sbias + c0 + o8 * 8 + 4);
+        const float4 b0 = lds_f4(sbias + c0 + o8 * 8), b1 = lds_f4(sbias + c0 + o8 * 8 + 4);
         const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
         float v[8];
 #pragma unroll
@@ -306,7 +337,7 @@ __device__ __forceinline__ bool epilogue_fast_ok(const ConvPtrs &q, const ConvPa
 template <bool STACKED>
 __device__ __forceinline__ void epilogue_fast_dispatch(const ConvPtrs &q, const ConvParams &p, uint32_t taddr, int c0, int b,
                                                        int y, int x, bool ok, int o_base, const float *sbias,
-                                                       float out_scale, float res_scale, const ResRegs *r1) {
+                                                       float out_scale, float res_scale, ResRegs *r1) {
     const bool oct = q.out_f32 != nullptr;
     if (oct) {
         if (p.act == 0) epilogue_fast_block<0, false, true, STACKED>(q, p, taddr, c0, b, y, x, ok, o_base, sbias, out_scale, res_scale, r1);

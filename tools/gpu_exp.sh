@@ -1,11 +1,9 @@
 #!/bin/bash
 O=gpurun_out
-for m in 0 1; do
-  for cfg in "H=640 CIN=64 COUT=64" "H=160 CIN=64 COUT=64" "H=320 CIN=128 COUT=128" "H=640 CIN=64 COUT=64 MODE=res" "H=640 CIN=3 COUT=64" "H=640 CIN=32 COUT=3 MODE=f32add"; do
-    echo "2cta=$m: $(env C2M_CONV_2CTA=$m $cfg N=5 timeout 300 python tools/conv_one.py 2>&1 | tail -1)"
-  done
-done > $O/r2h_conv.log 2>&1
-LAYER=all N=3 python tools/dcn_layers.py >> $O/r2h_conv.log 2>&1
-timeout 1200 python -m pytest tests -m gpu -q --timeout 600 -p no:cacheprovider -k "not corr and not feature_match and not search_on" 2>&1 | tail -5 > $O/r2h_t.log
-C2M_CONV_2CTA=0 python tools/gpu_breakdown.py > $O/r2h_breakdown.log 2>&1
-cat $O/r2h_conv.log; tail -3 $O/r2h_t.log; grep -E "ms/step|c2m::" $O/r2h_breakdown.log | cut -c1-60,150-250 | head -8
+for cfg in "H=640 CIN=64 COUT=64" "H=640 CIN=64 COUT=64 MODE=res" "H=160 CIN=64 COUT=64 MODE=res" "H=320 CIN=64 COUT=64 MODE=res"; do
+  echo "$(env $cfg N=5 timeout 300 python tools/conv_one.py 2>&1 | tail -1)"
+done > $O/r2j_conv.log 2>&1
+for pol in 5 13; do echo "policy $pol:"; C2M_DCN_POLICY=$pol LAYER=all N=3 python tools/dcn_layers.py 2>&1 | tail -3; done >> $O/r2j_conv.log 2>&1
+cat $O/r2j_conv.log
+bash tools/gpu_check.sh r2j tests benchfull
+LAYER=small N=1 ncu --set full --clock-control none --import-source on -k regex:dcn_umma -s 2 -c 1 -f -o $O/r2j_dcn_small python tools/dcn_layers.py > $O/r2j_ncu_dcn.log 2>&1
