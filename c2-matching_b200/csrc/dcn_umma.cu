@@ -63,8 +63,7 @@ struct DcnTc {
     int nstage, nbst;          // ring depths (activation stages, weight chunks); powers of two
     int nstage_shift;          // log2(nstage)
     int tg;                    // pixel tiles per work item (<= T)
-    int policy;                // 1 = input map evict-last, 2 = offsets / mask evict-first, 4 = streaming output stores,
-                               // 8 = prefetch the next unit's corners into L2
+    int policy;                // L2 policies: 1 = input map evict-last, 2 = offsets / mask evict-first, 4 = streaming output stores
     int sc_shift;              // log2(pre_scale) when the flow table is used (idx given, scale in {1,2,4,8}), else -1
     int tab_h, tab_w;          // flow-table cells per tile: 16/s + 2, 8/s + 2
     float inv_ref_gw, inv_scale;   // reciprocals for the exact float-assisted integer divisions
@@ -304,6 +303,7 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
         // cell of this thread's pixel inside a tile's flow table, before the tap shift (+2 halo cells)
         const int cell0 = d.sc_shift >= 0 ? ((mrow >> d.sc_shift) + 2) * d.tab_w + (mcol >> d.sc_shift) + 2 : 0;
         const float Hf = (float)p.H, Wf = (float)p.W;
+        struct Meta { float off_h, off_w, mr; };
         int ring = 0;                                       // stages issued by this CTA so far (all groups agree)
         int gi = 0;                                         // tile-group counter (table double buffer)
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++gi) {
@@ -367,23 +367,18 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
                 c_xoff = (g * d.opp + (ko - (d.opp_shift >= 0 ? (pair << d.opp_shift) : pair * d.opp))) * P * 8;
             };
 
-            // ---- metadata of unit (kc, t): raw offsets (+ pre-offset) and mask logit of this thread's pixel, plus the
-            // chunk constants the sampling needs (they are consumed one unit after they are fetched)
-            struct Meta { float off_h, off_w, mr, fy, fx; int y, x, base; bool live; };
-            struct Ctx { int o0, o1, o2, o3, base; float w0, w1, w2, w3; };
-            auto fetch = [&](int kc, int t, bool in_range, Meta &mt) {
-                mt.off_h = mt.off_w = mt.mr = mt.fy = mt.fx = 0.f;
-                mt.y = mt.x = mt.base = 0;
-                mt.live = false;
+            // ---- metadata of unit (kc, t): raw offsets (+ pre-offset) and mask logit of this thread's pixel
+            auto fetch = [&](int kc, int t, bool in_range, Meta &mt, int &y_out, int &x_out, int &b_out, bool &live) {
+                mt.off_h = mt.off_w = mt.mr = 0.f;
+                y_out = x_out = b_out = 0;
+                live = false;
                 if (!in_range) return;
                 if (kc != c_kc) set_kc(kc);
                 const int4 ti = tinfo[t];
                 const int b = ti.x, y = ti.y + mrow, xx = ti.z + mcol;
-                mt.live = c_valid && y < p.H && xx < p.W;
-                mt.y = y; mt.x = xx;
-                mt.base = b * x_img + (mt.live ? c_xoff : 0);       // element offset of the run's first octet plane
-                mt.fy = c_fy; mt.fx = c_fx;
-                if (!mt.live) return;
+                live = c_valid && y < p.H && xx < p.W;
+                y_out = y; x_out = xx; b_out = b;
+                if (!live) return;
                 const int pp = y * p.W + xx;
                 const float *omb = d.om + (size_t)b * om_img;
                 if (d.om_c8 > 0) {     // the (y, x) offset pair shares an octet: one 8-byte load
@@ -419,80 +414,50 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
                     }
                 }
             };
-            // ---- sampling point of a unit's (pixel, g, tap): dcn_v2_im2col_cuda.cu:25-54,172-190
-            auto sample = [&](const Meta &mt, Ctx &c) {
-                c.o0 = c.o1 = c.o2 = c.o3 = 0;
-                c.w0 = c.w1 = c.w2 = c.w3 = 0.f;
-                c.base = mt.base;
-                if (!mt.live) return;
-                const float h_im = ((float)mt.y + mt.fy) + mt.off_h;
-                const float w_im = ((float)mt.x + mt.fx) + mt.off_w;
-                if (h_im > -1.f && w_im > -1.f && h_im < Hf && w_im < Wf) {
-                    const float hf = floorf(h_im), wf = floorf(w_im);
-                    const int h_low = (int)hf, w_low = (int)wf;
-                    const float lh = h_im - hf, lw = w_im - wf;
-                    const float hh = 1.f - lh, hw = 1.f - lw;
-                    const bool tv = h_low >= 0, bv = h_low + 1 <= p.H - 1, lvv = w_low >= 0, rv = w_low + 1 <= p.W - 1;
-                    // sigmoid to ~2 ulp: the TC path is fp32-grade, not bit-exact; the mask is folded into the weights
-                    const float mk = d.mask ? mt.mr : __fdividef(1.f, 1.f + __expf(-mt.mr));
-                    const int r0 = h_low * W8 + w_low * 8;
-                    const float mh = hh * mk, ml = lh * mk;
-                    if (tv && lvv) { c.o0 = r0; c.w0 = mh * hw; }
-                    if (tv && rv) { c.o1 = r0 + 8; c.w1 = mh * lw; }
-                    if (bv && lvv) { c.o2 = r0 + W8; c.w2 = ml * hw; }
-                    if (bv && rv) { c.o3 = r0 + W8 + 8; c.w3 = ml * lw; }
-                }
-            };
-            // the gather is load-latency bound (ncu: long-scoreboard stalls dominate, ~40 % of the corner sectors come
-            // from DRAM because one image's input map (105 MB) exceeds what an L2 partition keeps): the NEXT unit's
-            // corners are pulled into L2 while the current unit is fetched and blended — no registers, no shared memory
-            auto prefetch_l2 = [&](const Ctx &c) {
-                const __half *xh = d.x_hi + c.base, *xl = d.x_lo + c.base;
-                for (int u = 0; u < L; ++u) {
-                    const int po = u * P * 8;
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(xh + po + c.o0));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(xh + po + c.o1));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(xh + po + c.o2));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(xh + po + c.o3));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(xl + po + c.o0));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(xl + po + c.o1));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(xl + po + c.o2));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(xl + po + c.o3));
-                }
-            };
 
-            // my units of this group: steps sg, sg + NG, ...; (kc, t) advanced incrementally.  Three-deep software
-            // pipeline: metadata of unit n+2 in flight, corners of unit n+1 being prefetched into L2, unit n fetched + blended
+            // my units of this group: steps sg, sg + NG, ...; (kc, t) advanced incrementally
             int kc = 0, t = sg;
             while (t >= nt) { t -= nt; ++kc; }
-            auto advance = [&](int &k, int &tt) {
-                tt += NG;
-                while (tt >= nt) { tt -= nt; ++k; }
-            };
-            Meta mnext;
-            Ctx cur, nxt;
-            fetch(kc, t, sg < n_steps, mnext);
-            sample(mnext, cur);
-            int kc1 = kc, t1 = t;
-            advance(kc1, t1);
-            fetch(kc1, t1, sg + NG < n_steps, mnext);
+            Meta mt, nx;
+            int y, ny, xx, nxx, b, nb;
+            bool lv, nlv;
+            fetch(kc, t, sg < n_steps, mt, y, xx, b, lv);
             for (int step = sg; step < n_steps; step += NG) {
-                // unit n+1: sampling point from its metadata (requested one iteration ago), corners -> L2
-                sample(mnext, nxt);
-                if (d.policy & 8) prefetch_l2(nxt);
-                // unit n+2: request metadata
-                advance(kc1, t1);
-                fetch(kc1, t1, step + 2 * NG < n_steps, mnext);
-                const __half *xh = d.x_hi + cur.base;
-                const __half *xl = d.x_lo + cur.base;
-                const float w0 = cur.w0, w1 = cur.w1, w2 = cur.w2, w3 = cur.w3;
-                const int o0 = cur.o0, o1 = cur.o1, o2 = cur.o2, o3 = cur.o3;
+                int nkc_ = kc, nt_ = t + NG;
+                while (nt_ >= nt) { nt_ -= nt; ++nkc_; }
+                // ---- sampling point of the unit's (pixel, g, tap): dcn_v2_im2col_cuda.cu:25-54,172-190
+                int o0 = 0, o1 = 0, o2 = 0, o3 = 0;
+                float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
+                const int xoff = c_xoff;                    // belongs to kc (set_kc(kc) ran in this unit's fetch)
+                if (lv) {
+                    const float h_im = ((float)y + c_fy) + mt.off_h;
+                    const float w_im = ((float)xx + c_fx) + mt.off_w;
+                    if (h_im > -1.f && w_im > -1.f && h_im < Hf && w_im < Wf) {
+                        const float hf = floorf(h_im), wf = floorf(w_im);
+                        const int h_low = (int)hf, w_low = (int)wf;
+                        const float lh = h_im - hf, lw = w_im - wf;
+                        const float hh = 1.f - lh, hw = 1.f - lw;
+                        const bool tv = h_low >= 0, bv = h_low + 1 <= p.H - 1, lvv = w_low >= 0, rv = w_low + 1 <= p.W - 1;
+                        // sigmoid to ~2 ulp: the TC path is fp32-grade, not bit-exact; the mask is folded into the weights
+                        const float mk = d.mask ? mt.mr : __fdividef(1.f, 1.f + __expf(-mt.mr));
+                        const int r0 = h_low * W8 + w_low * 8;
+                        const float mh = hh * mk, ml = lh * mk;
+                        if (tv && lvv) { o0 = r0; w0 = mh * hw; }
+                        if (tv && rv) { o1 = r0 + 8; w1 = mh * lw; }
+                        if (bv && lvv) { o2 = r0 + W8; w2 = ml * hw; }
+                        if (bv && rv) { o3 = r0 + W8 + 8; w3 = ml * lw; }
+                    }
+                }
+                const __half *xh = d.x_hi + (size_t)b * x_img + (lv ? xoff : 0);
+                const __half *xl = d.x_lo + (size_t)b * x_img + (lv ? xoff : 0);
                 const __half2 wh0 = __float2half2_rn(w0), wh1 = __float2half2_rn(w1), wh2 = __float2half2_rn(w2),
                               wh3 = __float2half2_rn(w3);
                 const int stage_idx = ring + step;
                 const int rs = stage_idx & nstage_mask;
                 const uint32_t rphase = (uint32_t)(stage_idx >> d.nstage_shift) & 1u;
                 uint8_t *sdst = sA + rs * A_STAGE + (slot * L) * A_OCT_B + m * 16;
+                // next unit's metadata goes out before this unit's corner fetches come back
+                fetch(nkc_, nt_, step + NG < n_steps, nx, ny, nxx, nb, nlv);
 #pragma unroll 1
                 for (int u = 0; u < L; ++u) {
                     // octet-planar operand: the 32 lanes of a warp (4 rows x 8 pixels) read 16 B each from runs of
@@ -533,7 +498,9 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full[rs]);
-                cur = nxt;
+                mt = nx; lv = nlv; y = ny; xx = nxx; b = nb;
+                kc = nkc_;
+                t = nt_;
             }
             ring += n_steps;
         }
@@ -657,7 +624,7 @@ extern "C" int c2m_dcn_v2_fused_tc(const c2m_dcn_tc_args *a, c2m_stream_t stream
     q.out_hi = reinterpret_cast<__half *>(a->out_hi); q.out_lo = reinterpret_cast<__half *>(a->out_lo);
     q.out_f32 = a->out_f32;
     DcnTc d;
-    d.policy = 13;     // 1 input evict-last | 4 streaming output stores | 8 L2 prefetch of the next unit (2: offsets evict-first)
+    d.policy = 5;      // measured (profiles/r02_dcn_experiments.md): hints change nothing beyond noise; 2 (offsets evict-first) costs 3 %
     if (const char *ev = getenv("C2M_DCN_POLICY")) d.policy = atoi(ev);     // tuning experiments
     p.cs = (d.policy & 4) ? 1 : 0;
     if (const char *ev = getenv("C2M_L2_PERSIST_MB")) {                      // experiment: L2 set-aside for evict-last lines
