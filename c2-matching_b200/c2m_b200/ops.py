@@ -238,6 +238,20 @@ class OctF32:
         return self.data.permute(0, 1, 4, 2, 3).reshape(B, c8 * 8, H, W)[:, :self.C].contiguous()
 
 
+def suggest_sa(amax, target_log2=12):
+    """Scale exponent for a PSA tensor whose largest magnitude is `amax`: amax * 2^sa ~ 2^target_log2 (fp16 tops out
+    at 65504 = 2^16, so 16x headroom; values below 2^-14 * 2^-sa lose their lo half to fp16 subnormals)."""
+    import math
+    if not (amax > 0) or not math.isfinite(amax):
+        return 0
+    return max(-14, min(24, target_log2 - math.ceil(math.log2(amax))))
+
+
+def psa_amax(p):
+    """Largest |value| of a PSA tensor (from its hi half: within 2^-11), as a Python float (synchronises)."""
+    return float(p.hi.abs().max()) * 2.0 ** (-p.sa)
+
+
 def psa_from_f32(x, sa=0):
     _require_cuda('x', x)
     B, C, H, W = x.shape
@@ -315,6 +329,9 @@ def invalidate_packs(obj):
     """Drop the cached packed weights of a tensor, or of every parameter of a module (needed after in-place
     edits through `.data`, which do not bump the tensor version)."""
     tensors = [obj] if isinstance(obj, torch.Tensor) else list(obj.parameters())
+    if not isinstance(obj, torch.Tensor):
+        for m in obj.modules():                 # calibrated PSA scale exponents of VGG trunks depend on the weights too
+            m.__dict__.pop('_c2m_sa', None)
     for t in tensors:
         d = getattr(t, '__dict__', None)
         if d is not None:

@@ -53,8 +53,9 @@ class RestorationPipeline:
         return self
 
     @torch.no_grad()
-    def forward(self, img_in_lq, img_in_up, img_ref, return_idx=False):
-        """Device tensors in, SR device tensor out."""
+    def forward(self, img_in_lq, img_in_up, img_ref, return_idx=False, check_finite=False):
+        """Device tensors in, SR device tensor out.  check_finite: synchronise and raise if the result contains inf / NaN
+        (a packed-split activation that left the fp16 range shows up there; off on the timed path)."""
         if not self._placed:
             self.place()
         prev = torch.backends.cudnn.allow_tf32
@@ -69,6 +70,9 @@ class RestorationPipeline:
             sr = self.net_g(img_in_lq, pre_offset, ref_feat)
         finally:
             torch.backends.cudnn.allow_tf32 = prev
+        if check_finite and not bool(torch.isfinite(sr).all()):
+            raise RuntimeError('non-finite SR output: an activation left the fp16 range of the packed-split layout '
+                               '(see c2m_b200.ops.suggest_sa) or the inputs were not finite')
         return (sr, pre_offset.max_idx) if return_idx else sr
 
     @torch.no_grad()

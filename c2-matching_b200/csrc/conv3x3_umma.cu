@@ -245,8 +245,11 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
             decode(item, b, t0, nt, slice);
             const int o_base = slice * p.N;
             asm volatile("bar.sync 1, 256;" ::: "memory");          // previous item's sbias readers are done
-            if (threadIdx.x - 128 < p.N) sbias[threadIdx.x - 128] =
-                (q.bias && o_base + (int)threadIdx.x - 128 < p.Cout) ? q.bias[o_base + threadIdx.x - 128] : 0.f;
+            if (threadIdx.x - 128 < p.N) {
+                const float bv = (q.bias && o_base + (int)threadIdx.x - 128 < p.Cout) ? q.bias[o_base + threadIdx.x - 128] : 0.f;
+                sbias[threadIdx.x - 128] = bv;
+                sbias[UC_NMAX + threadIdx.x - 128] = bv * so;       // pre-scaled copy for the specialised epilogue
+            }
             asm volatile("bar.sync 1, 256;" ::: "memory");
             const bool full_blk = fast && c0 + 32 <= p.N && o_base + c0 + 32 <= p.Cout;
             for (int t = 0; t < nt; ++t) {
@@ -282,8 +285,8 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + t * 2 * p.N;
                 if (c0 < p.N) {
                     if (full_blk)
-                        epilogue_fast_dispatch<true>(q, p, taddr, c0, b, y, x, ok, o_base, sbias, out_scale, res_scale,
-                                                     has1 ? &ra : nullptr);
+                        epilogue_fast_dispatch<true>(q, p, taddr, c0, b, y, x, ok, o_base, sbias + UC_NMAX, out_scale * so,
+                                                     res_scale * so, has1 ? &ra : nullptr);
                     else
                         epilogue_store_block(q, p, taddr, c0, b, y, x, ok, o_base, sbias, out_scale, res_scale, so,
                                              has1 ? &ra : nullptr);
@@ -555,8 +558,11 @@ conv3x3_umma2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
             decode(item, b, t0, nt, slice);
             const int o_base = slice * p.N;
             asm volatile("bar.sync 1, 256;" ::: "memory");          // previous item's sbias readers are done
-            if (threadIdx.x - 128 < p.N) sbias[threadIdx.x - 128] =
-                (q.bias && o_base + (int)threadIdx.x - 128 < p.Cout) ? q.bias[o_base + threadIdx.x - 128] : 0.f;
+            if (threadIdx.x - 128 < p.N) {
+                const float bv = (q.bias && o_base + (int)threadIdx.x - 128 < p.Cout) ? q.bias[o_base + threadIdx.x - 128] : 0.f;
+                sbias[threadIdx.x - 128] = bv;
+                sbias[UC_NMAX + threadIdx.x - 128] = bv * so;       // pre-scaled copy for the specialised epilogue
+            }
             asm volatile("bar.sync 1, 256;" ::: "memory");
             for (int t = 0; t < nt; ++t) {
                 const int tt = t0 + 2 * t + (int)rank;
@@ -575,8 +581,8 @@ conv3x3_umma2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + t * 2 * p.N;
                 if (c0 < p.N) {
                     if (fast && c0 + 32 <= p.N && o_base + c0 + 32 <= p.Cout)
-                        epilogue_fast_dispatch<true>(q, p, taddr, c0, b, y, x, ok, o_base, sbias, out_scale, res_scale,
-                                                     has1 ? &ra : nullptr);
+                        epilogue_fast_dispatch<true>(q, p, taddr, c0, b, y, x, ok, o_base, sbias + UC_NMAX, out_scale * so,
+                                                     res_scale * so, has1 ? &ra : nullptr);
                     else
                         epilogue_store_block(q, p, taddr, c0, b, y, x, ok, o_base, sbias, out_scale, res_scale, so,
                                              has1 ? &ra : nullptr);

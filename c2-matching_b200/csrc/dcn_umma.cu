@@ -247,7 +247,7 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
         const float out_scale = ldexpf(1.f, -(p.sa_in + sw));
         const float res_scale = 1.f;
         const float so = ldexpf(1.f, p.sa_out);
-        const bool fast = epilogue_fast_ok(q, p);
+        const bool fast = epilogue_fast_ok(q, p) && p.sa_out == 0;     // (this kernel does not pre-scale bias / factors)
         uint32_t tph = 0;
         int abase = 0;
         for (int i = e; i < p.N; i += 128) sbias[i] = (q.bias && i < p.Cout) ? q.bias[i] : 0.f;

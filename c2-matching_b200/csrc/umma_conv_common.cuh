@@ -227,7 +227,8 @@ __device__ __forceinline__ void epilogue_store_block(const ConvPtrs &q, const Co
 //   ACT 0 none / 1 ReLU / 2 LeakyReLU(0.1);  RES: one PSA residual (prefetched);  F32OCT: octet-planar fp32 output
 //   instead of PSA;  STACKED: accumulator columns [c, N + c) hold the x*W_hi and x*W_lo partial sums.
 // Preconditions (checked by the caller, warp-uniform): c0 + 32 <= N, o_base + c0 + 32 <= Cout, ps == 0, no res2,
-// sa_out == 0, exactly one output kind.
+// exactly one output kind.  A PSA output scale 2^sa_out is folded in by the caller: `sbias`, `out_scale` and `res_scale`
+// arrive pre-multiplied by it (ReLU / LeakyReLU commute with a positive scale), so it costs nothing per element.
 // ---------------------------------------------------------------------------------------------------------------
 // Branch-free residual prefetch of a FULL 32-column block (all four octets exist): the loads land directly in their
 // final registers.  (The generic prefetch_residual guards every octet with a branch; ptxas then copies each loaded
@@ -331,7 +332,7 @@ __device__ __forceinline__ void epilogue_fast_block(const ConvPtrs &q, const Con
 __device__ __forceinline__ bool epilogue_fast_ok(const ConvPtrs &q, const ConvParams &p) {
     const bool psa_only = q.out_hi && !q.out_f32;
     const bool oct_only = q.out_f32 && p.f32_mode == 2 && !q.out_hi;
-    return p.ps == 0 && !q.res2_hi && p.sa_out == 0 && !(p.dbg & 1) && (psa_only || (oct_only && !q.res_hi));
+    return p.ps == 0 && !q.res2_hi && !(p.dbg & 1) && (psa_only || (oct_only && !q.res_hi && p.sa_out == 0));
 }
 
 template <bool STACKED>

@@ -46,20 +46,32 @@ class ResidualBlockNoBN(nn.Module):
         return x + y if self.res_scale == 1 else x + y * self.res_scale
 
 
+_warned_small = False
+
+
 def fast_conv_enabled():
     """C2M_FAST_CONV=0 routes every plain convolution back to cuDNN (debug / A-B comparisons)."""
     import os
     return os.environ.get('C2M_FAST_CONV', '1') != '0'
 
 
-def psa_path_ok(x, *convs):
-    """True if the tcgen05 3x3 kernel can take over for tensor `x` [B,C,H,W] and these convs."""
+def psa_path_ok(x, *convs, cat_first=32):
+    """True if the tcgen05 3x3 kernel can take over for tensor `x` [B,C,H,W] and these convs.  `cat_first`: channel count of
+    the FIRST input of the two-input (concatenating) convolutions on the path — the kernel needs a multiple of 32 there."""
     if not (fast_conv_enabled() and x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled()):
         return False
     if x.shape[2] < 18 or x.shape[3] < 10:
+        # not silent: the tcgen05 kernel needs one 18x10 halo tile; smaller maps run the plain modules (cuDNN, exact fp32)
+        global _warned_small
+        if not _warned_small:
+            _warned_small = True
+            import logging
+            logging.getLogger('base').warning(
+                f'c2m: feature map {x.shape[2]}x{x.shape[3]} is smaller than one halo tile (18x10): the plain 3x3 convolutions '
+                'of this call run on nn.Conv2d (cuDNN, TF32 off), not on the tcgen05 kernel')
         return False
     return all(isinstance(c, nn.Conv2d) and c.kernel_size == (3, 3) and c.stride == (1, 1) and c.padding == (1, 1) and
-               c.dilation == (1, 1) and c.groups == 1 and c.weight.is_cuda for c in convs)
+               c.dilation == (1, 1) and c.groups == 1 and c.weight.is_cuda for c in convs) and cat_first % 32 == 0
 
 
 def conv_psa(conv, xp, act=None, **kw):

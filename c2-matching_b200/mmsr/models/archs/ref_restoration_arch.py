@@ -114,7 +114,10 @@ class RestorationNet(nn.Module):
     def forward(self, x, pre_offset, img_ref_feat):
         base = F.interpolate(x, None, 4, 'bilinear', False)
         ce, dr = self.content_extractor, self.dyn_agg_restore
-        if arch_util.psa_path_ok(x, ce.conv_first, dr.small_offset_conv1, dr.head_small[0], dr.tail_large[2]):
+        # the offset / head convolutions consume cat[content (ngf channels), ref]: ngf must be a multiple of 32 for the
+        # two-input tcgen05 convolution, otherwise the module path below runs
+        if arch_util.psa_path_ok(x, ce.conv_first, dr.small_offset_conv1, dr.head_small[0], dr.tail_large[2],
+                                 cat_first=ce.conv_first.out_channels):
             return dr.forward_psa(ce.forward_psa(x), pre_offset, img_ref_feat, base.contiguous())
         content_feat = ce(x)
         return dr(content_feat, pre_offset, img_ref_feat) + base

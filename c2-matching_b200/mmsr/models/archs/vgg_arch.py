@@ -173,7 +173,18 @@ def run_trunk(trunk, x, taps=(), want_last_f32=True, packed_taps=False):
                 got[name] = x
         return x, got
     got = {}
-    xp, xf = ops.psa_from_f32(x), None
+    # PSA scale exponents of the trunk's INTERNAL activations (tapped outputs stay at 0: their consumers — the DCN
+    # gather and the two-input convolutions — take exponent 0).  Calibrated on the first call from the activations'
+    # amax (one synchronising pass, then cached on the trunk), so that tensors with small magnitudes keep their lo
+    # halves out of the fp16 subnormal range and large ones keep 16x headroom below 65504.
+    sa_tab = getattr(trunk, '_c2m_sa', None)
+    calibrating = sa_tab is None
+    if calibrating:
+        sa_tab = {}
+    sa_in = sa_tab.get('__input__', 0)
+    if calibrating:
+        sa_in = sa_tab['__input__'] = ops.suggest_sa(float(x.abs().max()))
+    xp, xf = ops.psa_from_f32(x, sa_in), None
     i = 0
     while i < len(layers):
         name, layer = layers[i]
@@ -189,8 +200,16 @@ def run_trunk(trunk, x, taps=(), want_last_f32=True, packed_taps=False):
             if xp is None:
                 xp = ops.psa_from_f32(xf)
             # tapped features feed the DCN sampler, which gathers 8-channel octets: keep them channels-last
+            sa_out = 0 if (out_name in taps or not need_psa) else sa_tab.get(out_name, 0)
             r = ops.conv3x3_psa(xp, layer.weight, layer.bias, act='relu' if has_relu else None, psa_out=need_psa,
-                                out_f32=need_f32, channels_last=out_name in taps)
+                                out_f32=need_f32, channels_last=out_name in taps, sa_out=sa_out)
+            if calibrating and need_psa and out_name not in taps:
+                pr = r[0] if (need_psa and need_f32) else r
+                sa_new = ops.suggest_sa(ops.psa_amax(pr))
+                sa_tab[out_name] = sa_new
+                if sa_new != 0:      # redo this layer at its calibrated exponent so the first call already uses it
+                    r = ops.conv3x3_psa(xp, layer.weight, layer.bias, act='relu' if has_relu else None, psa_out=need_psa,
+                                        out_f32=need_f32, channels_last=out_name in taps, sa_out=sa_new)
             if need_psa and need_f32:
                 xp, xf = r
                 arch_util.attach_psa(xf, xp)
@@ -210,6 +229,11 @@ def run_trunk(trunk, x, taps=(), want_last_f32=True, packed_taps=False):
             i += 1
         else:
             raise RuntimeError(f'unexpected layer {name} in VGG trunk')
+    if calibrating:
+        try:
+            trunk._c2m_sa = sa_tab
+        except Exception:
+            pass
     if xf is None and (want_last_f32 or not packed_taps):
         xf = ops.psa_to_f32(xp)
     return xf, (PackedFeatures(got) if packed_taps else got)

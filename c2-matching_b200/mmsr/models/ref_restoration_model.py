@@ -90,6 +90,10 @@ class RefRestorationModel:
     # -- validation (ref_restoration_model.py:295-370): rank-sharded, batched, host work off the GPU's critical path
     def _score_image(self, sr, gt, meta, crop, save_dir):
         """CPU post-processing of one image: tensor2img, un-pad, PNG, PSNR / PSNR_Y / SSIM_Y (reference :306-360)."""
+        if not bool(torch.isfinite(sr).all()):
+            # packed-split activations are fp16 pairs: |x * 2^sa| must stay below 65504 (c2m_b200.ops.PSA)
+            raise RuntimeError(f"non-finite SR output for {meta['name']}: an activation left the fp16 range of the "
+                               'packed-split layout (ops.suggest_sa / PSA.sa) or the inputs were not finite')
         sr_img, gt_img = tensor2img([sr, gt])
         if meta['padding']:
             oh, ow = meta['original_size']

@@ -613,3 +613,69 @@ def test_non_square_pipeline_fast_vs_module_path(monkeypatch):
     assert tuple(sr_fast.shape) == (1, 3, 4 * lr_h, 4 * lr_w)
     assert int((idx_fast != idx_slow).sum()) <= 3
     _rel_ok(sr_fast, sr_slow, 1e-3)          # always: the module path is evaluated on the fast path's index map
+
+
+# ------------------------------------------------------------------------------- PSA dynamic range
+def test_psa_scale_exponent_and_range():
+    """The packed-split layout stores fp16 pairs of x * 2^sa.  (1) activations spanning 1e-4 ... 1e4 with Kaiming-scale
+    weights: <= 1e-5 of the output scale vs fp64, finite;  (2) a tensor that is tiny everywhere needs a scale exponent:
+    with ops.suggest_sa the same bar holds (with sa = 0 its lo halves fall into the fp16 subnormals);  (3) beyond the
+    fp16 range the result is non-finite and the pipeline-level check raises instead of returning garbage."""
+    from c2m_b200 import ops
+    rng = np.random.default_rng(7)
+    w = torch.from_numpy((rng.standard_normal((64, 64, 3, 3)) * np.sqrt(2.0 / 576)).astype(np.float32))
+    b = seeding.randn(3, (64,), 0.1)
+    wd, bd = w.to(DEV), b.to(DEV)
+
+    def run(x, sa_in, sa_out):
+        yp = ops.conv3x3_psa(ops.psa_from_f32(x.to(DEV), sa_in), wd, bd, act='lrelu', sa_out=sa_out)
+        want = F.leaky_relu(F.conv2d(x.double(), w.double(), b.double(), 1, 1), 0.1)
+        got = ops.psa_to_f32(yp).cpu().double()
+        return float((got - want).abs().max()) / float(want.abs().max()), bool(torch.isfinite(got).all()), float(want.abs().max())
+
+    # (1) wide range, exponent 0
+    mag = torch.from_numpy(10.0 ** rng.uniform(-4, 4, (1, 64, 40, 36))).float()
+    x = mag * torch.from_numpy(rng.choice([-1.0, 1.0], (1, 64, 40, 36))).float()
+    err, fin, _ = run(x, 0, 0)
+    assert fin and err <= 1e-5, err
+    # (2) tiny everywhere
+    xs = seeding.randn(5, (1, 64, 40, 36), 1e-4)
+    xs_out_scale = run(xs, 0, 0)[2]
+    sa_i, sa_o = ops.suggest_sa(float(xs.abs().max())), ops.suggest_sa(xs_out_scale + 0.1 * 0 + float(b.abs().max()))
+    assert sa_i >= 20
+    err_s, fin_s, _ = run(xs, sa_i, sa_o)
+    assert fin_s and err_s <= 1e-5, (err_s, sa_i, sa_o)
+    assert abs(ops.psa_amax(ops.psa_from_f32(xs.to(DEV), sa_i)) - float(xs.abs().max())) <= 1e-3 * float(xs.abs().max())
+    # (3) overflow is visible, not silent
+    xb = seeding.randn(6, (1, 64, 40, 36), 3e5)
+    _, fin_b, _ = run(xb, 0, 0)
+    assert not fin_b
+    err_b, fin_b2, _ = run(xb, ops.suggest_sa(float(xb.abs().max())), ops.suggest_sa(float(xb.abs().max()) * 3))
+    assert fin_b2 and err_b <= 1e-5, err_b
+
+
+def test_vgg_trunk_calibrates_nonzero_scale_exponents():
+    """run_trunk calibrates a PSA scale exponent per internal activation on its first call (tapped outputs stay at 0) and
+    the result still matches the plain modules; invalidate_packs drops the calibration."""
+    from c2m_b200 import ops
+    from mmsr.models.archs.vgg_arch import VGGFeatureExtractor
+    net = VGGFeatureExtractor(['relu1_1', 'relu2_1', 'relu3_1'], 'vgg19', pretrained=False)
+    net.load_state_dict(seeding.seeded_state_dict({k: tuple(v.shape) for k, v in net.state_dict().items()}, 5))
+    net.to(DEV).eval()
+    img = seeding.rand_image(72, (1, 3, 96, 80)).to(DEV)
+    with torch.no_grad():
+        fast = net(img)
+        sa = dict(net.vgg_net._c2m_sa)
+        assert any(v != 0 for k, v in sa.items()) and 'relu1_1' not in sa and 'relu2_1' not in sa, sa
+        fast2 = net(img)                               # second call: cached exponents, identical result
+        xn = (img - net.mean) / net.std
+        slow = {}
+        for name, layer in net.vgg_net.named_children():
+            xn = torch.relu(xn) if isinstance(layer, torch.nn.ReLU) else layer(xn)
+            if name in ('relu1_1', 'relu2_1', 'relu3_1'):
+                slow[name] = xn
+    for k in slow:
+        _rel_ok(fast[k], slow[k], 2e-5)
+        assert torch.equal(fast[k], fast2[k])
+    ops.invalidate_packs(net)
+    assert not hasattr(net.vgg_net, '_c2m_sa')

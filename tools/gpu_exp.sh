@@ -1,9 +1,8 @@
 #!/bin/bash
 O=gpurun_out
-for cfg in "H=640 CIN=64 COUT=64" "H=640 CIN=64 COUT=64 MODE=res" "H=160 CIN=64 COUT=64 MODE=res" "H=320 CIN=64 COUT=64 MODE=res"; do
-  echo "$(env $cfg N=5 timeout 300 python tools/conv_one.py 2>&1 | tail -1)"
-done > $O/r2j_conv.log 2>&1
-for pol in 5 13; do echo "policy $pol:"; C2M_DCN_POLICY=$pol LAYER=all N=3 python tools/dcn_layers.py 2>&1 | tail -3; done >> $O/r2j_conv.log 2>&1
-cat $O/r2j_conv.log
-bash tools/gpu_check.sh r2j tests benchfull
-LAYER=small N=1 ncu --set full --clock-control none --import-source on -k regex:dcn_umma -s 2 -c 1 -f -o $O/r2j_dcn_small python tools/dcn_layers.py > $O/r2j_ncu_dcn.log 2>&1
+bash tools/gpu_check.sh r2l tests bench
+bash tools/gpu_traffic.sh r2l
+for cfg in "6 6 4" "12 8 4" "16 12 4" "12 8 8"; do set -- $cfg
+  python bench.py --workload config5 --loader-workers $1 --post-workers $2 --eval-batch $3 2> $O/r2l_cfg5_$1_$2_$3.err | tail -1 > $O/r2l_cfg5_$1_$2_$3.json
+  python -c "import json;j=json.load(open('$O/r2l_cfg5_$1_$2_$3.json'));print('cfg5 workers $1 post $2 batch $3:', round(j['value'],1),'img/s', j['limiting_stage'], j['per_rank'])"
+done
