@@ -19,12 +19,12 @@ def tensor2img(tensor, out_type=np.uint8, min_max=(0, 1)):
             from torchvision.utils import make_grid
             t = make_grid(t, nrow=int(math.sqrt(t.size(0))), normalize=False)
         if t.dim() == 3:
-            img = t.numpy()[[2, 1, 0]].transpose(1, 2, 0)
-        elif t.dim() == 2:
-            img = t.numpy()
-        else:
+            # RGB CHW -> BGR HWC and the x255 rounding in torch (contiguous, GIL-free; same float32 arithmetic and the
+            # same round-half-to-even as numpy's fancy-index + strided multiply, which took 80 ms per 640x640 image)
+            t = t.flip(0).permute(1, 2, 0).contiguous()
+        elif t.dim() != 2:
             raise TypeError(f'Only support 4D, 3D or 2D tensor. But received with dimension: {t.dim()}')
         if out_type == np.uint8:
-            img = (img * 255.0).round()
-        outs.append(img)
+            t = (t * 255.0).round()
+        outs.append(t.numpy())
     return outs[0] if len(outs) == 1 else outs
