@@ -45,7 +45,7 @@ class DcnTcArgs(ctypes.Structure):
                 ('out_hi', ctypes.c_void_p), ('out_lo', ctypes.c_void_p), ('sa_out', ctypes.c_int),
                 ('out_f32', ctypes.c_void_p), ('os_b', ctypes.c_longlong), ('os_c', ctypes.c_longlong),
                 ('os_y', ctypes.c_longlong), ('os_x', ctypes.c_longlong), ('om_octets', ctypes.c_int),
-                ('mask', ctypes.c_void_p)]
+                ('mask', ctypes.c_void_p), ('x_il', ctypes.c_void_p)]
 
 
 SYMBOLS = {
@@ -59,6 +59,7 @@ SYMBOLS = {
     'c2m_psa_to_f32': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 5 + [c_f32p, c_f32p] +
                        [ctypes.c_longlong] * 4 + [ctypes.c_void_p]),
     'c2m_conv3x3': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    'c2m_psa_interleave': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 4 + [ctypes.c_void_p] * 2),
     'c2m_psa_maxpool2': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 4 + [ctypes.c_void_p] * 3),
     'c2m_dcn_v2_im2col_f32': (ctypes.c_int, [c_f32p] * 3 + [ctypes.POINTER(DcnShape), c_f32p, ctypes.c_void_p]),
     'c2m_dcn_v2_col2im_coord_f32': (ctypes.c_int, [c_f32p] * 4 + [ctypes.POINTER(DcnShape), c_f32p, c_f32p, ctypes.c_void_p]),
@@ -86,7 +87,7 @@ class C2MError(RuntimeError):
     pass
 
 
-EXPECTED_ABI = 3      # c2m_abi_version() the ctypes structs above mirror (include/c2m_sm100.h)
+EXPECTED_ABI = 4      # c2m_abi_version() the ctypes structs above mirror (include/c2m_sm100.h)
 
 
 def lib():

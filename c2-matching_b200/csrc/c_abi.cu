@@ -94,7 +94,7 @@ static void carve(CorrWorkspace &ws, const CorrGeom &g, uint8_t *base) {
 
 using namespace c2m;
 
-extern "C" int c2m_abi_version(void) { return 3; }   // 3: c2m_dcn_tc_args.mask; 2: out_f32_octets / om_octets
+extern "C" int c2m_abi_version(void) { return 4; }   // 4: c2m_dcn_tc_args.x_il + c2m_psa_interleave; 3: .mask; 2: out_f32_octets / om_octets
 extern "C" const char *c2m_last_error(void) { return g_err; }
 extern "C" unsigned long long c2m_launch_count(void) { return g_launches.load(); }
 

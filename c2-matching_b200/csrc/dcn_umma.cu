@@ -48,6 +48,7 @@ constexpr int W_HDR = 256;
 
 struct DcnTc {
     const __half *x_hi, *x_lo; // input in the packed-split layout [B][C/8][H][W][8] (value = hi + lo)
+    const __half *x_il;        // or (non-null) the same values interleaved [B][C/8][H][W][hi 8 | lo 8]: one sector per corner
     int C8;
     const float *om;           // [B, 3*dg*9, H, W], or octet-planar [B][om_c8][H][W][8] when om_c8 > 0
     int om_c8;
@@ -102,6 +103,12 @@ __device__ __forceinline__ uint4 ldg_keep_v4(const void *ptr, uint64_t pol) {
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                  : "l"(ptr), "l"(pol));
     return v;
+}
+// one (pixel, octet) of the interleaved operand: 32 B = one sector, one 256-bit load
+__device__ __forceinline__ void ldg_keep_v8(const void *ptr, uint64_t pol, uint4 &h, uint4 &l) {
+    asm volatile("ld.global.nc.L2::cache_hint.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8], %9;"
+                 : "=r"(h.x), "=r"(h.y), "=r"(h.z), "=r"(h.w), "=r"(l.x), "=r"(l.y), "=r"(l.z), "=r"(l.w)
+                 : "l"(ptr), "l"(pol));
 }
 __device__ __forceinline__ float2 ldg_stream_f2(const float *ptr, uint64_t pol) {
     float2 v;
@@ -463,10 +470,19 @@ dcn_umma_kernel(const ConvPtrs q, const ConvParams p, const DcnTc d) {
                     // octet-planar operand: the 32 lanes of a warp (4 rows x 8 pixels) read 16 B each from runs of
                     // adjacent pixels (8 lines per request instead of 32 with a channels-last fp32 input)
                     const int po = u * P * 8;
-                    const uint4 ch0 = ldg_keep_v4(xh + po + o0, pol_keep), ch1 = ldg_keep_v4(xh + po + o1, pol_keep);
-                    const uint4 ch2 = ldg_keep_v4(xh + po + o2, pol_keep), ch3 = ldg_keep_v4(xh + po + o3, pol_keep);
-                    const uint4 cl0 = ldg_keep_v4(xl + po + o0, pol_keep), cl1 = ldg_keep_v4(xl + po + o1, pol_keep);
-                    const uint4 cl2 = ldg_keep_v4(xl + po + o2, pol_keep), cl3 = ldg_keep_v4(xl + po + o3, pol_keep);
+                    uint4 ch0, ch1, ch2, ch3, cl0, cl1, cl2, cl3;
+                    if (d.x_il) {                          // element offsets double in the interleaved operand
+                        const __half *xi = d.x_il + 2 * ((size_t)b * x_img + (lv ? xoff : 0) + po);
+                        ldg_keep_v8(xi + 2 * o0, pol_keep, ch0, cl0);
+                        ldg_keep_v8(xi + 2 * o1, pol_keep, ch1, cl1);
+                        ldg_keep_v8(xi + 2 * o2, pol_keep, ch2, cl2);
+                        ldg_keep_v8(xi + 2 * o3, pol_keep, ch3, cl3);
+                    } else {
+                        ch0 = ldg_keep_v4(xh + po + o0, pol_keep); ch1 = ldg_keep_v4(xh + po + o1, pol_keep);
+                        ch2 = ldg_keep_v4(xh + po + o2, pol_keep); ch3 = ldg_keep_v4(xh + po + o3, pol_keep);
+                        cl0 = ldg_keep_v4(xl + po + o0, pol_keep); cl1 = ldg_keep_v4(xl + po + o1, pol_keep);
+                        cl2 = ldg_keep_v4(xl + po + o2, pol_keep); cl3 = ldg_keep_v4(xl + po + o3, pol_keep);
+                    }
                     // ---- blend, modulate, split.  value = hi + lo: the hi halves are blended in fp32, the lo halves
                     // (|lo| <= 2^-11 |value|) in packed fp16 — their rounding lands at 2^-22 of the value
                     const __half2 *hp0 = reinterpret_cast<const __half2 *>(&ch0), *hp1 = reinterpret_cast<const __half2 *>(&ch1);
@@ -595,7 +611,8 @@ extern "C" int c2m_dcn_tc_pack_weights_f32(const float *w, int C, int Cout, int 
 }
 
 extern "C" int c2m_dcn_v2_fused_tc(const c2m_dcn_tc_args *a, c2m_stream_t stream) {
-    C2M_CHECK_ARG(a && a->x_hi && a->x_lo && a->om && a->packed_w, "dcn_v2_fused_tc: null pointer");
+    C2M_CHECK_ARG(a && ((a->x_hi && a->x_lo) || a->x_il) && a->om && a->packed_w, "dcn_v2_fused_tc: null pointer");
+    C2M_CHECK_ARG(!a->x_il || (reinterpret_cast<uintptr_t>(a->x_il) & 31) == 0, "dcn_v2_fused_tc: x_il must be 32 B aligned");
     C2M_CHECK_ARG(a->B > 0 && a->H > 0 && a->W > 0, "dcn_v2_fused_tc: bad shape");
     C2M_CHECK_ARG(c2m_dcn_tc_supported(a->C, a->Cout, a->dg), "dcn_v2_fused_tc: C=%d dg=%d unsupported", a->C, a->dg);
     C2M_CHECK_ARG(!(a->pre == nullptr && a->idx != nullptr) || (a->gh > 0 && a->gw > 0 && a->ref_gw > 0 && a->pre_scale > 0),
@@ -632,6 +649,8 @@ extern "C" int c2m_dcn_v2_fused_tc(const c2m_dcn_tc_args *a, c2m_stream_t stream
         if (!done) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)atoi(ev) << 20); done = 1; }
     }
     d.x_hi = reinterpret_cast<const __half *>(a->x_hi); d.x_lo = reinterpret_cast<const __half *>(a->x_lo);
+    d.x_il = reinterpret_cast<const __half *>(a->x_il);
+    if (!d.x_hi) { d.x_hi = d.x_il; d.x_lo = d.x_il; }     // never dereferenced when x_il is set; keep pointers valid
     d.C8 = a->C / 8;
     d.om_c8 = a->om_octets ? (27 * a->dg + 7) / 8 : 0;
     C2M_CHECK_ARG(!a->om_octets || (reinterpret_cast<uintptr_t>(a->om) & 7) == 0, "dcn_v2_fused_tc: om must be 8 B aligned");

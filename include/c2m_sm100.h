@@ -43,7 +43,7 @@ enum {
     C2M_ERR_UNSUPPORTED = 4   /* no sm_100 device / driver entry point missing */
 };
 
-int c2m_abi_version(void);      /* 3 since c2m_dcn_tc_args.mask (2: out_f32_octets / om_octets) */
+int c2m_abi_version(void);      /* 4 since c2m_dcn_tc_args.x_il / c2m_psa_interleave (3: .mask; 2: out_f32_octets / om_octets) */
 const char *c2m_last_error(void);
 
 /* --- correlation / index_map --------------------------------------------------------------
@@ -143,6 +143,8 @@ int c2m_psa_from_f32(const float *x, int B, int C, int H, int W, long long xs_b,
 int c2m_psa_to_f32(const void *hi, const void *lo, int B, int C, int H, int W, int sa, const float *add, float *out,
                    long long os_b, long long os_c, long long os_y, long long os_x, c2m_stream_t stream);
 int c2m_conv3x3(const c2m_conv3x3_args *args, c2m_stream_t stream);
+/* hi / lo planes -> interleaved [B][ceil(C/8)][H][W][hi 8 | lo 8] (the DCN gather's preferred operand). */
+int c2m_psa_interleave(const void *hi, const void *lo, int B, int C, int H, int W, void *out, c2m_stream_t stream);
 /* MaxPool2d(2, 2) on a PSA tensor (floor semantics: odd trailing row / column dropped), PSA result. */
 int c2m_psa_maxpool2(const void *hi, const void *lo, int B, int C, int H, int W, void *out_hi, void *out_lo,
                      c2m_stream_t stream);
@@ -167,6 +169,9 @@ typedef struct {
     const float *mask;           /* != NULL: the `_ext.dcn_v2_forward` contract (DCNv2/src/dcn_v2.h:9-22) — `om` is the
                                   * FINAL offset tensor [B,2*dg*9,H,W], `mask` the FINAL modulation [B,dg*9,H,W]
                                   * (no sigmoid applied); pre, idx and om_octets must be unset */
+    const void *x_il;            /* != NULL: the input with the two halves of a (pixel, octet) adjacent,
+                                  * fp16 [B][C/8][H][W][hi 8 | lo 8] (c2m_psa_interleave), 32 B aligned; x_hi / x_lo may
+                                  * then be NULL.  A corner fetch is one 32 B sector instead of two. */
 } c2m_dcn_tc_args;
 
 int c2m_dcn_tc_supported(int C, int Cout, int dg);

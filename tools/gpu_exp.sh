@@ -1,6 +1,9 @@
 #!/bin/bash
 O=gpurun_out
-for cfg in "6 6 4" "8 12 4" "12 16 4" "12 24 4"; do set -- $cfg
-  python bench.py --workload config5 --loader-workers $1 --post-workers $2 --eval-batch $3 2> $O/r2m_cfg5_$1_$2_$3.err | tail -1 > $O/r2m_cfg5_$1_$2_$3.json
-  python -c "import json;j=json.load(open('$O/r2m_cfg5_$1_$2_$3.json'));print('cfg5 workers $1 post $2 batch $3:', round(j['value'],1),'img/s', j['limiting_stage'], j['per_rank'])"
-done
+for il in 0 1; do echo "interleave=$il:"; C2M_DCN_INTERLEAVE=$il LAYER=all N=3 python tools/dcn_layers.py 2>&1 | tail -3; done > $O/r2o_dcn.log 2>&1
+python tools/micro4.py 2>/dev/null | cut -c1-200 >> $O/r2o_dcn.log
+cat $O/r2o_dcn.log
+timeout 900 python -m pytest tests -m gpu -q --timeout 600 -p no:cacheprovider -k "dcn" 2>&1 | tail -4
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-micro > $O/r2o_bench.json 2> $O/r2o_bench.err
+python -c "
+import json;j=json.loads(open('$O/r2o_bench.json').read().strip().splitlines()[-1]);print(j['value'], j['e2e']['value']);[print(k,round(v['ms_per_step'],2)) for k,v in j['roofline']['per_kernel_class'].items()]"
