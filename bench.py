@@ -355,7 +355,7 @@ def run_config5(args, rank, world, local_rank):
         torch.distributed.barrier()
     entry.build()
     opt = {'name': 'config5', 'suffix': None, 'scale': 4, 'crop_border': None, 'dist': dist_on, 'is_train': False,
-           'post_workers': args.post_workers,
+           'post_workers': args.post_workers, 'metrics_device': args.metrics_device,
            'network_g': {'type': 'RestorationNet', 'ngf': 64, 'n_blocks': 16, 'groups': 8},
            'network_map': {'type': 'CorrespondenceGenerationArch', 'patch_size': 3, 'stride': 1,
                            'vgg_layer_list': ['relu1_1', 'relu2_1', 'relu3_1'], 'vgg_type': 'vgg19', 'vgg_pretrained': False},
@@ -365,11 +365,13 @@ def run_config5(args, rank, world, local_rank):
         net.load_state_dict(sd, strict=True)
     dopt = {'name': 'config5_synth', 'type': 'SyntheticRefDataset', 'phase': 'test', 'num': args.pairs, 'gt_size': 4 * LR,
             'ref_size': REF, 'scale': 4, 'num_workers': args.loader_workers, 'batch_size': args.eval_batch,
-            'prefetch_factor': 2}
+            'prefetch_factor': 2, 'per_sample_workers': not args.per_batch_workers}
     dset = create_dataset(dopt)
     # warm-up on a few pairs (weight packing, allocator, loader worker start-up are not part of the metric)
     wopt = dict(dopt, num=max(2, args.eval_batch) * world)
-    model.validation(create_dataloader(create_dataset(wopt), wopt, dist=dist_on), 0)
+    wloader = create_dataloader(create_dataset(wopt), wopt, dist=dist_on)
+    model.validation(wloader, 0)
+    getattr(wloader, 'close', lambda: None)()
 
     def barrier():
         if dist_on:
@@ -386,7 +388,9 @@ def run_config5(args, rank, world, local_rank):
     barrier()
     wall = max_over_ranks(time.perf_counter() - t0, dev)
     clocks = sampler.stop() if sampler else None
-    stage = torch.tensor([res['rank_loader_wait_s'], res['rank_submit_s'], res['rank_wall_s'], float(res['rank_images'])],
+    getattr(loader, 'close', lambda: None)()
+    stage = torch.tensor([res['rank_loader_wait_s'], res['rank_submit_s'], res['rank_wall_s'], float(res['rank_images']),
+                          res['rank_gpu_busy_s']],
                          dtype=torch.float64, device=dev)
     if dist_on:
         stages = [torch.zeros_like(stage) for _ in range(world)]
@@ -395,19 +399,24 @@ def run_config5(args, rank, world, local_rank):
         stages = [stage]
     if rank == 0:
         per_rank = [{'images': int(s[3]), 'wall_s': round(float(s[2]), 3), 'loader_wait_s': round(float(s[0]), 3),
-                     'forward_submit_s': round(float(s[1]), 3)} for s in stages]
+                     'forward_submit_s': round(float(s[1]), 3), 'gpu_busy_s': round(float(s[4]), 3)} for s in stages]
         worst = max(per_rank, key=lambda r: r['wall_s'])
-        limiting = ('host loader (GPU waits for decoded pairs)' if worst['loader_wait_s'] > 0.3 * worst['wall_s'] else
-                    'host post-processing / submit' if worst['forward_submit_s'] > 0.8 * worst['wall_s'] else 'GPU forward')
+        limiting = ('GPU forward (device busy %d %% of the wall time)' % round(100 * worst['gpu_busy_s'] / worst['wall_s'])
+                    if worst['gpu_busy_s'] > 0.7 * worst['wall_s'] else
+                    'host loader (GPU waits for decoded pairs)' if worst['loader_wait_s'] > 0.3 * worst['wall_s'] else
+                    'host post-processing / submit')
         physical, logical = host_cores()
         print(json.dumps({
             'metric': 'SR images/sec, sharded evaluation of 126 CUFED5-shape pairs (config 5)', 'value': args.pairs / wall,
             'unit': 'images/s', 'n_gpus': world, 'steps': 1, 'warmup': 1, 'ms_per_step': wall * 1e3, 'higher_is_better': True,
             'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': f'config5: {args.pairs} synthetic pairs (GT 640x640, Ref 500x500 zero-padded), RefRestorationModel.validation: '
-                                   'dataset decode + PIL bicubic in loader workers, rank::world index sharding, same-shape batches, '
-                                   'forward, async D2H, PSNR/PSNR_Y/SSIM_Y on a thread pool, final all-gather of the metric rows',
-                       'eval_batch': args.eval_batch, 'loader_workers_per_rank': args.loader_workers,
+                                   'dataset decode + PIL bicubic in loader workers ('
+                                   + ('one batch' if args.per_batch_workers else 'one pair') + ' per worker task), rank::world index '
+                                   'sharding, same-shape batches, forward, PSNR/PSNR_Y/SSIM_Y '
+                                   + ('on the GPU (float64, reference definitions)' if args.metrics_device == 'cuda' else
+                                      'on a host thread pool after an async D2H copy') + ', final all-gather of the metric rows',
+                       'metrics_device': args.metrics_device, 'eval_batch': args.eval_batch, 'loader_workers_per_rank': args.loader_workers,
                        'post_workers_per_rank': args.post_workers, 'host_cores': {'physical': physical, 'logical': logical},
                        'parallelism': f'dp{world} (pair list sharded rank::world; collective = metric all-gather only)'},
             'validation': {k: res[k] for k in ('psnr', 'psnr_y', 'ssim_y', 'n')}, 'per_rank': per_rank,
@@ -431,8 +440,11 @@ def main():
                     help='config2 (default, the headline metric) or config5: sharded evaluation of 126 pairs')
     ap.add_argument('--pairs', type=int, default=126)
     ap.add_argument('--eval-batch', type=int, default=4)
-    ap.add_argument('--loader-workers', type=int, default=6)
+    ap.add_argument('--loader-workers', type=int, default=10)
     ap.add_argument('--post-workers', type=int, default=6)
+    ap.add_argument('--metrics-device', choices=['cuda', 'cpu'], default='cuda',
+                    help="config5: where PSNR/SSIM run ('cpu' = the reference's numpy/cv2 arithmetic on a thread pool)")
+    ap.add_argument('--per-batch-workers', action='store_true', help='config5: one BATCH per loader-worker task')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))

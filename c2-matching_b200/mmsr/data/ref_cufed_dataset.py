@@ -73,7 +73,8 @@ class RefCUFEDDataset(data.Dataset):
         return len(self.paths)
 
     def pair_shape(self, i):
-        """(H, W) of the padded HR tensors of pair i, from the image headers only (batch bucketing key)."""
+        """(padded H, padded W, GT h, GT w) of pair i from the image headers only — the batch bucketing key: every
+        tensor of the sample dict has a shape determined by it (`img_in` is the UN-padded ground truth)."""
         from PIL import Image
         s = self.opt['scale']
         dims = []
@@ -81,7 +82,7 @@ class RefCUFEDDataset(data.Dataset):
             with Image.open(p) as im:
                 w, h = im.size
             dims.append((h - h % s, w - w % s))
-        return max(dims[0][0], dims[1][0]), max(dims[0][1], dims[1][1])
+        return (max(dims[0][0], dims[1][0]), max(dims[0][1], dims[1][1])) + dims[0]
 
     def __getitem__(self, i):
         import cv2
@@ -106,8 +107,9 @@ class SyntheticRefDataset(data.Dataset):
 
     def pair_shape(self, i):
         s = self.opt.get('scale', 4)
-        m = max(self.gt - self.gt % s, self.ref - self.ref % s)
-        return m, m
+        g = self.gt - self.gt % s
+        m = max(g, self.ref - self.ref % s)
+        return m, m, g, g
 
     def __getitem__(self, i):
         rng = np.random.default_rng(1234 + i)

@@ -15,7 +15,7 @@ import torch
 
 from c2m_b200.dist import gather_rows
 from mmsr.models import networks
-from mmsr.utils import metrics
+from mmsr.utils import metrics, metrics_torch
 from mmsr.utils.util import tensor2img
 
 logger = logging.getLogger('base')
@@ -88,20 +88,34 @@ class RefRestorationModel:
         raise NotImplementedError('training is outside the B200 hot-path scope')
 
     # -- validation (ref_restoration_model.py:295-370): rank-sharded, batched, host work off the GPU's critical path
+    # packed-split activations are fp16 pairs: |x * 2^sa| must stay below 65504 (c2m_b200.ops.PSA)
+    _NONFINITE = ('non-finite SR output for {}: an activation left the fp16 range of the packed-split layout '
+                  '(ops.suggest_sa / PSA.sa) or the inputs were not finite')
+
+    def _png_name(self, meta):
+        return f"{meta['name']}_{self.opt['name']}" + (f"_{self.opt['suffix']}" if self.opt.get('suffix') else '') + '.png'
+
+    def _save_image(self, sr, meta, save_dir):
+        """PNG only (the metrics were computed on the GPU)."""
+        import cv2
+        sr_img = tensor2img(sr)
+        if meta['padding']:
+            oh, ow = meta['original_size']
+            sr_img = sr_img[:oh, :ow]
+        cv2.imwrite(osp.join(save_dir, self._png_name(meta)), sr_img)
+        return None
+
     def _score_image(self, sr, gt, meta, crop, save_dir):
         """CPU post-processing of one image: tensor2img, un-pad, PNG, PSNR / PSNR_Y / SSIM_Y (reference :306-360)."""
         if not bool(torch.isfinite(sr).all()):
-            # packed-split activations are fp16 pairs: |x * 2^sa| must stay below 65504 (c2m_b200.ops.PSA)
-            raise RuntimeError(f"non-finite SR output for {meta['name']}: an activation left the fp16 range of the "
-                               'packed-split layout (ops.suggest_sa / PSA.sa) or the inputs were not finite')
+            raise RuntimeError(self._NONFINITE.format(meta['name']))
         sr_img, gt_img = tensor2img([sr, gt])
         if meta['padding']:
             oh, ow = meta['original_size']
             sr_img, gt_img = sr_img[:oh, :ow], gt_img[:oh, :ow]
         if save_dir is not None:
             import cv2
-            name = f"{meta['name']}_{self.opt['name']}" + (f"_{self.opt['suffix']}" if self.opt.get('suffix') else '')
-            cv2.imwrite(osp.join(save_dir, name + '.png'), sr_img)
+            cv2.imwrite(osp.join(save_dir, self._png_name(meta)), sr_img)
         psnr = metrics.psnr(sr_img, gt_img, crop_border=crop)
         sr_y = metrics.bgr2ycbcr(sr_img / 255., only_y=True)
         gt_y = metrics.bgr2ycbcr(gt_img / 255., only_y=True)
@@ -110,10 +124,14 @@ class RefRestorationModel:
         logger.info(f"# img {meta['name']} # PSNR: {psnr:.4e} # PSNR_Y: {psnr_y:.4e} # SSIM_Y: {ssim_y:.4e}.")
         return (meta['index'], psnr, psnr_y, ssim_y)
 
-    def validation(self, dataloader, current_iter, tb_logger=None, save_img=False, post_workers=None):
+    def validation(self, dataloader, current_iter, tb_logger=None, save_img=False, post_workers=None,
+                   metrics_device=None):
         """The loader hands this rank only ITS pairs (ShardedEvalSampler), batched by shape; per batch the GPU runs
-        one forward, the SR images go to a pinned ring with an async D2H copy, and a thread pool turns them into
-        metrics / PNGs while the next batch is on the GPU.  The ranks' metric rows are all-gathered at the end."""
+        one forward.  `metrics_device` (`opt['metrics_device']`, default 'cuda'): 'cuda' scores the batch where it is
+        (`utils/metrics_torch.py`: same definitions and dtypes as the host metrics, equal to ~1e-14) and nothing
+        returns to the host but four numbers per image; 'cpu' is the reference's own arithmetic (`utils/metrics.py`,
+        cv2) on a thread pool fed through a pinned ring with an async D2H copy.  PNGs (`save_img`) always go through
+        the pinned ring + thread pool.  The ranks' metric rows are all-gathered at the end."""
         import time
         from concurrent.futures import ThreadPoolExecutor
         dist_on = torch.distributed.is_available() and torch.distributed.is_initialized()
@@ -121,11 +139,16 @@ class RefRestorationModel:
         crop = self.opt.get('crop_border')
         if crop is None:
             crop = self.opt.get('scale', 4)
+        metrics_device = metrics_device or self.opt.get('metrics_device') or 'cuda'
+        if metrics_device not in ('cuda', 'cpu'):
+            raise ValueError(f"metrics_device must be 'cuda' or 'cpu', got {metrics_device!r}")
+        on_gpu = metrics_device == 'cuda'
         dataset_name = dataloader.dataset.opt['name']
         save_dir = None
         if save_img:
             save_dir = osp.join(self.opt['path']['visualization'], dataset_name)
             os.makedirs(save_dir, exist_ok=True)
+        host_post = save_img or not on_gpu
         batches = getattr(getattr(dataloader, 'batch_sampler', None), 'batches', None)
         pool = ThreadPoolExecutor(max_workers=int(post_workers or self.opt.get('post_workers') or 4))
         # the post-processing threads are the parallelism: torch / OpenCV intra-op pools on top of them oversubscribe
@@ -138,6 +161,7 @@ class RefRestorationModel:
         except Exception:
             pass
         ring, futures = [], []          # ring of (pinned buffer, in-flight futures using it)
+        gpu_rows, metas, spans = [], [], []
         depth = 3
         t_load = t_gpu = 0.0
         n_img = 0
@@ -152,49 +176,77 @@ class RefRestorationModel:
                 break
             t_load += time.perf_counter() - tl
             tg = time.perf_counter()
-            # the ground truth stays on the host: metrics are computed there (the reference ships it to the GPU and back)
-            self.feed_data({k: v for k, v in val_data.items() if k != 'img_in'})
+            ev0 = torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            # host metrics: the ground truth stays on the host (the reference ships it to the GPU and back)
+            self.feed_data({k: v for k, v in val_data.items() if torch.is_tensor(v) and (on_gpu or k != 'img_in')})
+            stage = val_data.get('_slot')
+            if stage is not None:       # PairBatcher staging buffers: reusable once these H2D copies are done
+                stage['event'] = torch.cuda.Event()
+                stage['event'].record()
             self.test()
             out = self.output
             n = out.shape[0]
-            # pinned slot: reuse the oldest buffer of this shape once its consumers are done
-            slot = None
-            if len(ring) >= depth:
-                buf, futs = ring.pop(0)
-                for f in futs:
-                    f.result()
-                if buf.shape == out.shape:
-                    slot = buf
-            if slot is None:
-                slot = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
-            slot.copy_(out, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record()
-            t_gpu += time.perf_counter() - tg
-            gts = val_data['img_in']
             idxs = batches[bi] if batches is not None else list(range(n_img, n_img + n))
-            futs = []
-            for k in range(n):
-                pad = val_data.get('padding')
-                osz = val_data.get('original_size')
-                meta = {'index': int(idxs[k]), 'name': osp.splitext(osp.basename(val_data['lq_path'][k]))[0],
-                        'padding': bool(pad[k]) if pad is not None else False,
-                        'original_size': tuple(int(v) for v in osz[k][:2]) if osz is not None else None}
-
-                def job(k=k, meta=meta, ev=ev, slot=slot, gts=gts):
-                    ev.synchronize()
-                    return self._score_image(slot[k], gts[k], meta, crop, save_dir)
-                futs.append(pool.submit(job))
-            ring.append((slot, futs))
-            futures += futs
+            pad = val_data.get('padding')
+            osz = val_data.get('original_size')
+            bmeta = [{'index': int(idxs[k]), 'name': osp.splitext(osp.basename(val_data['lq_path'][k]))[0],
+                      'padding': bool(pad[k]) if pad is not None else False,
+                      'original_size': tuple(int(v) for v in osz[k][:2]) if osz is not None else None}
+                     for k in range(n)]
+            if on_gpu:
+                for k, meta in enumerate(bmeta):
+                    gpu_rows.append(metrics_torch.score_image(
+                        out[k], self.gt[k], crop, meta['original_size'] if meta['padding'] else None))
+                metas += bmeta
+            if host_post:
+                # pinned slot: reuse the oldest buffer of this shape once its consumers are done
+                slot = None
+                if len(ring) >= depth:
+                    buf, futs = ring.pop(0)
+                    for f in futs:
+                        f.result()
+                    if buf.shape == out.shape:
+                        slot = buf
+                if slot is None:
+                    slot = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+                slot.copy_(out, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                gts = None if on_gpu else val_data['img_in']
+                futs = []
+                for k, meta in enumerate(bmeta):
+                    def job(k=k, meta=meta, ev=ev, slot=slot, gts=gts):
+                        ev.synchronize()
+                        if gts is None:
+                            return self._save_image(slot[k], meta, save_dir)
+                        return self._score_image(slot[k], gts[k], meta, crop, save_dir)
+                    futs.append(pool.submit(job))
+                ring.append((slot, futs))
+                futures += futs
+            ev1 = torch.cuda.Event(enable_timing=True)
+            ev1.record()
+            spans.append((ev0, ev1))
+            t_gpu += time.perf_counter() - tg
             n_img += n
             bi += 1
         rows = [f.result() for f in futures]
         pool.shutdown()
         torch.set_num_threads(prev_threads)
+        if on_gpu:
+            t = torch.stack(gpu_rows) if gpu_rows else torch.zeros(0, 4, dtype=torch.float64, device=self.device)
+            host = t.cpu()              # the one synchronising read of the validation
+            for meta, (p, py, sy, fin) in zip(metas, host.tolist()):
+                if not fin:
+                    raise RuntimeError(self._NONFINITE.format(meta['name']))
+                logger.info(f"# img {meta['name']} # PSNR: {p:.4e} # PSNR_Y: {py:.4e} # SSIM_Y: {sy:.4e}.")
+            t = torch.cat([torch.tensor([m['index'] for m in metas], dtype=torch.float64,
+                                        device=self.device)[:, None], t[:, :3]], 1)
+        else:
+            t = torch.tensor(rows, dtype=torch.float64, device=self.device).reshape(-1, 4)
         torch.cuda.synchronize(self.device)
         wall = time.perf_counter() - t0
-        t = torch.tensor(rows, dtype=torch.float64, device=self.device).reshape(-1, 4)
+        gpu_busy = sum(a.elapsed_time(b) for a, b in spans) * 1e-3      # H2D + forward (+ metrics) per batch, on the device
         t = gather_rows(t)
         avg = t[:, 1:].mean(0).tolist() if t.numel() else [float('nan')] * 3
         if rank == 0:
@@ -204,5 +256,5 @@ class RefRestorationModel:
                     tb_logger.add_scalar(k, v, current_iter)
         self.last_validation = {'psnr': avg[0], 'psnr_y': avg[1], 'ssim_y': avg[2], 'n': int(t.shape[0]),
                                 'rank_images': n_img, 'rank_wall_s': wall, 'rank_loader_wait_s': t_load,
-                                'rank_submit_s': t_gpu}
+                                'rank_submit_s': t_gpu, 'rank_gpu_busy_s': gpu_busy, 'metrics_device': metrics_device}
         return self.last_validation

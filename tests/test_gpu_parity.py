@@ -335,6 +335,31 @@ def test_cli_runs_on_synthetic_yaml(tmp_path):
     assert '# Validation synth # PSNR:' in r.stderr + r.stdout
 
 
+def test_validation_gpu_metrics_equal_host_metrics(tmp_path):
+    """N1: `validation` with device-side scores + per-pair loader workers returns the same PSNR / PSNR_Y / SSIM_Y as
+    the host path (the reference's numpy / cv2 arithmetic, per-batch loader), incl. zero-padded pairs and PNG output."""
+    import bench
+    from mmsr.data import create_dataloader, create_dataset
+    from mmsr.models.ref_restoration_model import RefRestorationModel
+    opt = {'name': 'valtest', 'suffix': None, 'scale': 4, 'crop_border': None, 'dist': False, 'is_train': False,
+           'network_g': {'type': 'RestorationNet', 'ngf': 64, 'n_blocks': 16, 'groups': 8},
+           'network_map': {'type': 'CorrespondenceGenerationArch', 'patch_size': 3, 'stride': 1,
+                           'vgg_layer_list': ['relu1_1', 'relu2_1', 'relu3_1'], 'vgg_type': 'vgg19', 'vgg_pretrained': False},
+           'network_extractor': {'type': 'ContrasExtractorSep'}, 'path': {'visualization': str(tmp_path)}}
+    model = RefRestorationModel(opt)
+    for net, sd in zip((model.net_extractor, model.net_map, model.net_g), bench.seeded_weights()):
+        net.load_state_dict(sd, strict=True)
+    dopt = {'name': 'synth', 'type': 'SyntheticRefDataset', 'phase': 'test', 'num': 5, 'gt_size': 80, 'ref_size': 96,
+            'scale': 4, 'batch_size': 2, 'num_workers': 2}
+    dset = create_dataset(dopt)
+    a = dict(model.validation(create_dataloader(dset, dopt), 0, save_img=True, metrics_device='cuda'))
+    b = dict(model.validation(create_dataloader(dset, dict(dopt, per_sample_workers=False)), 0, metrics_device='cpu'))
+    assert a['n'] == b['n'] == 5 and a['metrics_device'] == 'cuda' and b['metrics_device'] == 'cpu'
+    for k in ('psnr', 'psnr_y', 'ssim_y'):
+        assert abs(a[k] - b[k]) <= 1e-9 * max(1.0, abs(b[k])), (k, a[k], b[k])
+    assert len(list((tmp_path / 'synth').glob('*.png'))) == 5
+
+
 # ------------------------------------------------------------------------------- tcgen05 3x3 conv
 @pytest.mark.parametrize('cfg', [(2, 64, 64, 40, 44, 'relu', False), (1, 64, 64, 37, 29, None, True),
                                  (1, 64, 32, 32, 32, 'lrelu', False), (1, 32, 3, 48, 40, None, False),

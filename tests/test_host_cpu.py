@@ -319,3 +319,86 @@ def test_sharded_eval_sampler_and_shape_buckets():
             assert len(batch['lq_path']) == batch['img_in'].shape[0] <= 3
             seen += batch['lq_path']
     assert sorted(seen) == [f'synthetic_{i:04d}.png' for i in range(7)]
+
+
+def test_pair_batcher_equals_batch_loader():
+    """N1: per-sample worker tasks + consumer-side stacking (`PairBatcher`) deliver exactly the batches of the
+    per-batch `DataLoader(batch_sampler=...)`, in the same order, with worker processes too."""
+    from mmsr.data import PairBatcher, create_dataloader, create_dataset
+    opt = {'name': 'synth', 'type': 'SyntheticRefDataset', 'num': 9, 'gt_size': 32, 'ref_size': 24, 'num_workers': 0,
+           'batch_size': 4, 'scale': 4}
+    dset = create_dataset(opt)
+    ref = list(create_dataloader(dset, dict(opt, per_sample_workers=False)))
+    for workers in (0, 2):
+        loader = create_dataloader(dset, dict(opt, num_workers=workers))
+        assert isinstance(loader, PairBatcher) and len(loader) == len(ref) == 3
+        assert loader.dataset is dset and loader.batch_sampler.batches == [[0, 1, 2, 3], [4, 5, 6, 7], [8]]
+        n = 0
+        for got, want in zip(loader, ref):
+            for k, v in want.items():
+                if torch.is_tensor(v):
+                    assert got[k].shape == v.shape and torch.equal(got[k], v), k     # compare before the slot is reused
+                else:
+                    assert list(got[k]) == list(v), k
+            assert ('_slot' in got) == (workers > 0)
+            n += 1
+        assert n == 3
+        if workers:
+            # an abandoned pass leaves nothing behind: the next pass starts clean and delivers the same batches
+            it = iter(loader)
+            next(it)
+            it.close()
+            again = [b['lq_path'] for b in loader]
+            assert again == [list(b['lq_path']) for b in ref]
+            loader.close()
+            with pytest.raises(RuntimeError, match='closed'):
+                next(iter(loader))
+
+
+def test_pair_batcher_reports_worker_errors_and_mixed_shapes():
+    import torch.utils.data as tud
+    from mmsr.data import PairBatcher
+
+    class Broken(tud.Dataset):
+        opt = {'name': 'broken'}
+
+        def __len__(self):
+            return 4
+
+        def __getitem__(self, i):
+            if i == 2:
+                raise ValueError('cannot decode pair 2')
+            return {'img_in': torch.zeros(3, 8 + 4 * (i == 1), 8), 'lq_path': f'{i}.png'}
+
+    loader = PairBatcher(Broken(), [[0], [2]], num_workers=1)
+    with pytest.raises(RuntimeError, match='cannot decode pair 2'):
+        list(loader)
+    loader.close()
+    loader = PairBatcher(Broken(), [[0, 1]], num_workers=2)
+    with pytest.raises(RuntimeError, match='differ in shape'):
+        list(loader)
+    loader.close()
+
+
+def test_metrics_torch_matches_host_metrics():
+    """The device-side scores (`metrics_torch.score_image`) follow the reference's metric definitions step by step:
+    equal to the numpy / cv2 versions to ~1e-12 incl. crop, un-padding and the non-finite flag."""
+    from mmsr.utils import metrics, metrics_torch
+    from mmsr.utils.util import tensor2img
+    g = torch.Generator().manual_seed(7)
+    gt = torch.rand(3, 72, 88, generator=g)
+    sr = gt + 0.04 * torch.randn(3, 72, 88, generator=g)
+    for crop, valid in ((4, None), (0, None), (4, (66, 81))):
+        got = metrics_torch.score_image(sr, gt, crop, valid).tolist()
+        a, b = tensor2img([sr, gt])
+        if valid:
+            a, b = a[:valid[0], :valid[1]], b[:valid[0], :valid[1]]
+        ya, yb = metrics.bgr2ycbcr(a / 255., only_y=True), metrics.bgr2ycbcr(b / 255., only_y=True)
+        want = (metrics.psnr(a, b, crop_border=crop), metrics.psnr(ya * 255, yb * 255, crop_border=crop),
+                metrics.ssim(ya * 255, yb * 255, crop_border=crop))
+        assert all(abs(x - y) <= 1e-11 * max(1.0, abs(y)) for x, y in zip(got, want)), (got, want)
+        assert got[3] == 1.0
+    assert metrics_torch.score_image(gt, gt, 4)[0].item() == float('inf')
+    bad = sr.clone()
+    bad[1, 5, 5] = float('nan')
+    assert metrics_torch.score_image(bad, gt, 4)[3].item() == 0.0
