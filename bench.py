@@ -285,7 +285,9 @@ def run_ours(args, rank, world, local_rank):
                 traffic_shape = tj['dominant_shape']
         except Exception:
             pass
-        issued = {'conv3x3': 3.0, 'corr_search': 3.0, 'dcn': 3.0}[dom]
+        # conv / dcn: three split products per algorithmic product.  corr: only the three ROW taps are MMAs (1/3 of the
+        # nine-tap flops), x3 split products, x(16/14)^2 for the halo columns of the 16-px blocks = 1.31
+        issued = {'conv3x3': 3.0, 'corr_search': 3.0 / 3.0 * (16.0 / 14.0) ** 2, 'dcn': 3.0}[dom]
         roofline = {'bound': 'tensor', 'kernel': name, 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
                     'frac': achieved / peak, 'traffic': traffic, 'traffic_dominant_shape': traffic_shape,
                     'peak_source': peak_src,
@@ -295,8 +297,9 @@ def run_ours(args, rank, world, local_rank):
                     'hbm_gbps_at_algorithmic_bytes': r['bytes'] / (r['ms'] / 1e3) / 1e9,
                     'issued_over_algorithmic_mma': issued,
                     'note': 'fp32-grade results from fp16 tensor cores: every product is issued as split hi/lo '
-                            'partial products (hi*hi + hi*lo + lo*hi = x3 issued MMA work), so the '
-                            'tensor-pipe busy fraction is `issued_over_algorithmic_mma` x `frac`',
+                            'partial products (hi*hi + hi*lo + lo*hi = x3 issued MMA work; the search issues only its '
+                            'row taps as MMAs and sums the column taps in the epilogue), so the tensor-pipe busy '
+                            'fraction is about `issued_over_algorithmic_mma` x `frac`',
                     'per_kernel_class': classes}
         cpu = parity = micro = None
         if world == 1 and not args.no_cpu_baseline:
