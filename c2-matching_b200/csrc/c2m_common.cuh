@@ -150,6 +150,18 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Single-thread issue with split descriptor words (inside `if (elect_one())`).
+__device__ __forceinline__ void umma_f16_1(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                           uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // Warp-uniform issue: called by ALL 32 lanes of the issuing warp under uniform control flow; one lane, elected inside
 // the asm, issues.  With `if (lane == 0) { ... umma_f16(...) }` ptxas wraps every MMA in an ELECT / R2UR.BROADCAST /
 // BRA.U.ANY loop (~11 SASS instructions, ~80 cycles per MMA measured) — longer than a 128x64x16 MMA occupies the pipe.

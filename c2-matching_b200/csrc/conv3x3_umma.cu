@@ -203,20 +203,32 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                         const uint32_t da_hi = (uint32_t)(ROW_B >> 4) | (1u << 14);
                         const uint32_t db_lo0 = ((w_st & 0x3FFFF) >> 4) | ((b_lbo >> 4) << 16);
                         const uint32_t db_hi = (128u >> 4) | (1u << 14);
+                        // ONE elected thread issues the tile's 36 MMAs as straight-line code: inside `if (elect_one())` ptxas
+                        // emits plain UTCHMMAs with the constant operands (descriptor high words, idesc, accumulator) moved
+                        // to uniform registers once, instead of an elect + five R2UR moves in front of every MMA
+                        if (elect_one()) {
+                            const uint32_t b_row = (3 * KOCT * b_lbo) >> 4;
+#pragma unroll 1
+                            for (int dy = 0; dy < 3; ++dy) {
+                                const uint32_t ar = dy * ((A_C * 16) >> 4), br = db_lo0 + dy * b_row;
 #pragma unroll
-                        for (int tap = 0; tap < 9; ++tap) {
+                                for (int dx = 0; dx < 3; ++dx) {
 #pragma unroll
-                            for (int j = 0; j < KOCT / 2; ++j) {
-                                const uint32_t ao = (((tap / 3) * A_C + tap % 3) * 16 + j * 2 * A_OCT_B) >> 4;
-                                const uint32_t bo = ((tap * KOCT + j * 2) * b_lbo) >> 4;
-                                // x_hi * [W_hi | W_lo]  (N = 2N)  +  x_lo * W_hi  (first N rows only)
-                                umma_f16_w(d, dah_lo + ao, da_hi, db_lo0 + bo, db_hi, idesc, (kc | tap | j) != 0);
-                                umma_f16_w(d, dal_lo + ao, da_hi, db_lo0 + bo, db_hi, idesc_lo, 1);
+                                    for (int j = 0; j < KOCT / 2; ++j) {
+                                        const uint32_t ao = ar + ((dx * 16 + j * 2 * A_OCT_B) >> 4);
+                                        const uint32_t bo = ((dx * KOCT + j * 2) * b_lbo) >> 4;
+                                        // x_hi * [W_hi | W_lo]  (N = 2N)  +  x_lo * W_hi  (first N rows only)
+                                        umma_f16_1(d, dah_lo + ao, da_hi, br + bo, db_hi, idesc, (kc | dy | dx | j) != 0);
+                                        umma_f16_1(d, dal_lo + ao, da_hi, br + bo, db_hi, idesc_lo, 1);
+                                    }
+                                }
                             }
+                            umma_commit(&empty[stage]);
+                            if (kc == p.nkc - 1) umma_commit(&tfull[t]);
                         }
-                        umma_commit_w(&empty[stage]);
+                        __syncwarp();
                         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-                        if (kc == p.nkc - 1) { umma_commit_w(&tfull[t]); tph ^= 1u << t; }
+                        if (kc == p.nkc - 1) tph ^= 1u << t;
                     }
                     if (!w_resident) umma_commit_w(&bempty[bst]);
                     if (++bst == NBST) { bst = 0; bphase ^= 1; }
