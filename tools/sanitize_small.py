@@ -26,5 +26,16 @@ c = ops.conv3x3_psa(a, w, b, residual=xp, residual2=a)
 wbig = seeding.randn(7, (256, 128, 3, 3), 0.05).to(dev)
 d = ops.conv3x3_psa(xp, wbig, None, x2=a, act='lrelu', pixel_shuffle=2)
 e = ops.conv3x3_psa(xp, wbig[:216, :64].contiguous(), None, psa_out=False, out_f32=True)
+# the literal `_ext` boundary on the tensor-core route, the max-pool, the PSA round trip and the interleaved DCN operand
+import _ext
+off = seeding.randn(8, (1, 144, 24, 24), 2.0).to(dev)
+msk = torch.sigmoid(seeding.randn(9, (1, 72, 24, 24)).to(dev))
+y3 = _ext.dcn_v2_forward(x, w, b, off, msk, 3, 3, 1, 1, 1, 1, 1, 1, 8)
+mp = ops.psa_maxpool2(xp)
+xi = ops.psa_interleave(xp)
+back = ops.psa_to_f32(a)
+# a search that overflows its candidate lists (constant features: every score ties) -> exhaustive re-scan kernels
+flat = torch.ones(1, 64, 20, 22, device=dev)
+c2m.corr_argmax(flat, flat, norm_input=True, l2norm=True)
 torch.cuda.synchronize()
 print('ok', float((y1 - y2).abs().max()), tuple(d.shape), tuple(e.shape))
