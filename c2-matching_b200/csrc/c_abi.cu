@@ -138,10 +138,12 @@ extern "C" int c2m_corr_argmax_f32(const float *fin, const float *fref, int B, i
         }
         ws.nchunk = corr_umma_pick_nchunk(g, sms);
         corr_umma_chunk_geom(g, ws.nchunk, cg);
-        // |approx - exact| <= 2^-22 * (K/16 + 3) * ||P_q|| * ||P_r|| * rinv_r  (K/16 tcgen05 instructions
-        // feed each score, 1 fp32 ulp of (|acc| + sum|products|) each, + the 2^-22 operand split); the window is
-        // twice that (best and candidate both err), times 2 of slack for the tensor core's internal alignment
-        window_coef = ldexpf(1.f, -20) * (float)((K + 15) / 16 + 3);
+        // the search scores (q_hi + q_lo) . r_hi.  |approx - exact| <= E = [2^-11 + 2^-22 (K/16 + 3)] ||P_q||
+        // ||P_r|| rinv_r: 2^-11 = fp16 rounding of the Ref operand (Cauchy-Schwarz over the patch), K/16 tcgen05
+        // instructions feed each score with 1 fp32 ulp of (|acc| + sum|products|) each, + the query's 2^-22 split.
+        // Window = 2E for the rounding part (best and candidate both err; 1 % margin for the fp16 subnormal range) and 4E
+        // for the accumulation part (x2 of slack for the tensor core's internal alignment).
+        window_coef = 1.01f * ldexpf(1.f, -10) + ldexpf(1.f, -20) * (float)((K + 15) / 16 + 3);
     } else {
         int n = ceil_div(4 * 148, g.B * ceil_div(g.NQ, 64));
         const int ntile = ceil_div(g.NR, 64);

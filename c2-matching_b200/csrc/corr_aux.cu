@@ -4,6 +4,9 @@
 //
 // Reference semantics restated: mmsr/models/archs/ref_map_util.py:26-86 (feature_match_index) and
 // mmsr/models/archs/corres_generation_arch.py:56-58 (F.normalize over channels).
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
 #include "corr_internal.cuh"
 
 namespace c2m {
@@ -181,7 +184,7 @@ __global__ void __launch_bounds__(256) search_generic_kernel(const float *__rest
     __shared__ int qpix[GS_T];
     __shared__ int rpix[GS_T];
     __shared__ float rsc[GS_T];
-    struct Red { float v[CORR_TOPK]; int i[CORR_TOPK]; float dropped; };      // 36 B
+    struct Red { float v[GEN_TOPK]; int i[GEN_TOPK]; float dropped; };      // 36 B
     __shared__ Red red[GS_T][16];
 
     const int b = blockIdx.z, chunk = blockIdx.y;
@@ -198,8 +201,8 @@ __global__ void __launch_bounds__(256) search_generic_kernel(const float *__rest
     const int per = ceil_div(ceil_div(g.NR, GS_T), nchunk) * GS_T;
     const int r_begin = chunk * per, r_end = min(g.NR, r_begin + per);
 
-    float cv[4][CORR_TOPK], cdrop[4];
-    int ci[4][CORR_TOPK];
+    float cv[4][GEN_TOPK], cdrop[4];
+    int ci[4][GEN_TOPK];
 #pragma unroll
     for (int i = 0; i < 4; ++i) { cand_init(cv[i], ci[i]); cdrop[i] = -INFINITY; }
 
@@ -264,20 +267,20 @@ __global__ void __launch_bounds__(256) search_generic_kernel(const float *__rest
     for (int i = 0; i < 4; ++i) {
         Red c;
 #pragma unroll
-        for (int k = 0; k < CORR_TOPK; ++k) { c.v[k] = cv[i][k]; c.i[k] = ci[i][k]; }
+        for (int k = 0; k < GEN_TOPK; ++k) { c.v[k] = cv[i][k]; c.i[k] = ci[i][k]; }
         c.dropped = cdrop[i];
         red[ty * 4 + i][tx] = c;
     }
     __syncthreads();
     if (t < GS_T && q0 + t < g.NQ) {
-        float av[CORR_TOPK], adrop = -INFINITY;
-        int ai[CORR_TOPK];
+        float av[GEN_TOPK], adrop = -INFINITY;
+        int ai[GEN_TOPK];
         cand_init(av, ai);
         for (int k = 0; k < 16; ++k) {
             const Red c = red[t][k];
             adrop = fmaxf(adrop, c.dropped);
 #pragma unroll
-            for (int j = 0; j < CORR_TOPK; ++j)
+            for (int j = 0; j < GEN_TOPK; ++j)
                 if (c.i[j] != 0x7fffffff) cand_push(c.v[j], c.i[j], av, ai, adrop);
         }
         part[((size_t)b * nchunk + chunk) * g.NQ + q0 + t] = cand_pack(av, ai, adrop);
@@ -558,6 +561,18 @@ int corr_rescore_launch(const CorrGeom &g, const CorrWorkspace &ws, const CorrCh
     rescore_kernel<<<grid, 256, 0, st>>>(ws.p32_in, ws.p32_ref, ws.part, g, ws.nchunk, window_coef, ws.max_pn_bits,
                                          is_norm, ws.best, ws.qnorm, ws.ovf, ws.ovf_count);
     C2M_LAUNCH_CHECK("rescore_kernel");
+    if (getenv("C2M_CORR_DEBUG")) {                 // diagnostics only: how many (query, chunk-mask) entries overflowed
+        unsigned n_ovf = 0;
+        cudaStreamSynchronize(st);
+        cudaMemcpy(&n_ovf, ws.ovf_count, sizeof n_ovf, cudaMemcpyDeviceToHost);
+        std::vector<CorrOverflow> h(n_ovf < 4096 ? n_ovf : 4096);
+        if (!h.empty()) cudaMemcpy(h.data(), ws.ovf, h.size() * sizeof(CorrOverflow), cudaMemcpyDeviceToHost);
+        unsigned long long bits = 0;
+        for (auto &e : h) bits += __builtin_popcount(e.chunks);
+        fprintf(stderr, "[c2m corr] queries %d, chunks %d, window_coef %.3e, overflow entries %u, flagged chunks in the first %zu: %llu\n",
+                g.B * g.NQ, ws.nchunk, window_coef, n_ovf, h.size(), bits);
+        for (size_t i = 0; i < h.size() && i < 6; ++i) fprintf(stderr, "   q %d mask %08x\n", h[i].query, h[i].chunks);
+    }
     // fp32 prefilter of the re-scan: query patch in shared memory when it fits (it does for every model shape)
     const int K = g.Cp * g.patch * g.patch;
     const int qs_floats = K * 4 <= 48 * 1024 ? K : 0;

@@ -10,7 +10,7 @@
 //                            K-major no-swizzle core-matrix layout with rows 16 B apart.
 //   ss    [B][HW]            fp32 per-pixel sum of squares of p32 (for the patch norms).
 //   rinv  [B][NR]            fp32 1 / (sqrt(sum_{patch} ss) + 1e-5)   (1 when !is_norm)
-//   part  [B][nchunk][NQ]    Candidate: approximate top-4 of each query over one Ref chunk (nchunk <= 32).
+//   part  [B][nchunk][NQ]    Candidate: approximate top-8 (tcgen05) / top-4 (FFMA) of each query over one Ref chunk (nchunk <= 32).
 //   ovf   [B*NQ]             (query, chunk bit mask) of the (query, chunk) pairs whose top-2 list may be incomplete:
 //                            the exhaustive pass re-scans those chunks exactly (see corr_aux.cu).
 #pragma once
@@ -18,7 +18,9 @@
 
 namespace c2m {
 
-constexpr int CORR_TOPK = 4;      // candidates kept per (query, Ref chunk) by the searches
+constexpr int CORR_TOPK = 8;      // candidate slots per (query, Ref chunk): the tcgen05 search fills all of them (its window is
+                                  // 2^-10-wide because the Ref operand is a plain fp16 rounding), the FFMA search GEN_TOPK
+constexpr int GEN_TOPK = 4;
 struct __align__(16) Candidate {
     float v[CORR_TOPK];           // approximate scores, best first
     int i[CORR_TOPK];             // Ref patch indices (-1 = empty slot)
@@ -65,40 +67,43 @@ struct CorrWorkspace {
     size_t total_bytes;
 };
 
-// Sorted top-4 insert with a record of what falls off the list: `dropped` ends up as the largest score the chunk
+// Sorted top-K insert with a record of what falls off the list: `dropped` ends up as the largest score the chunk
 // produced that is not in v[] (scores that never made it, and entries pushed out).  Strict '>' — ties beyond the
 // list count as dropped, and the rescoring pass re-scans a chunk exhaustively whenever `dropped` reaches the
 // window, so neither ties nor the list length can lose the true argmax.
-__device__ __forceinline__ void cand_push(float s, int r, float (&v)[CORR_TOPK], int (&i)[CORR_TOPK], float &dropped) {
-    if (!(s > v[3])) {
+template <int K>
+__device__ __forceinline__ void cand_push(float s, int r, float (&v)[K], int (&i)[K], float &dropped) {
+    if (!(s > v[K - 1])) {
         dropped = fmaxf(dropped, s);
         return;
     }
-    dropped = fmaxf(dropped, v[3]);
-    if (s > v[2]) {
-        v[3] = v[2]; i[3] = i[2];
-        if (s > v[1]) {
-            v[2] = v[1]; i[2] = i[1];
-            if (s > v[0]) {
-                v[1] = v[0]; i[1] = i[0]; v[0] = s; i[0] = r;
-            } else {
-                v[1] = s; i[1] = r;
-            }
-        } else {
-            v[2] = s; i[2] = r;
-        }
-    } else {
-        v[3] = s; i[3] = r;
+    dropped = fmaxf(dropped, v[K - 1]);
+    v[K - 1] = s;
+    i[K - 1] = r;
+#pragma unroll
+    for (int k = K - 1; k > 0; --k) {           // bubble up past strictly smaller entries (stable: ties stay behind)
+        const bool up = v[k] > v[k - 1];
+        const float tv = v[k - 1];
+        const int ti = i[k - 1];
+        v[k - 1] = up ? v[k] : tv;
+        i[k - 1] = up ? i[k] : ti;
+        v[k] = up ? tv : v[k];
+        i[k] = up ? ti : i[k];
     }
 }
-__device__ __forceinline__ void cand_init(float (&v)[CORR_TOPK], int (&i)[CORR_TOPK]) {
+template <int K>
+__device__ __forceinline__ void cand_init(float (&v)[K], int (&i)[K]) {
 #pragma unroll
-    for (int k = 0; k < CORR_TOPK; ++k) { v[k] = -INFINITY; i[k] = 0x7fffffff; }
+    for (int k = 0; k < K; ++k) { v[k] = -INFINITY; i[k] = 0x7fffffff; }
 }
-__device__ __forceinline__ Candidate cand_pack(const float (&v)[CORR_TOPK], const int (&i)[CORR_TOPK], float dropped) {
+template <int K>
+__device__ __forceinline__ Candidate cand_pack(const float (&v)[K], const int (&i)[K], float dropped) {
     Candidate c;
 #pragma unroll
-    for (int k = 0; k < CORR_TOPK; ++k) { c.v[k] = v[k]; c.i[k] = i[k] == 0x7fffffff ? -1 : i[k]; }
+    for (int k = 0; k < CORR_TOPK; ++k) {
+        c.v[k] = k < K ? v[k < K ? k : 0] : -INFINITY;
+        c.i[k] = k < K ? (i[k < K ? k : 0] == 0x7fffffff ? -1 : i[k < K ? k : 0]) : -1;
+    }
     c.dropped = dropped;
     c.pad[0] = c.pad[1] = c.pad[2] = 0.f;
     return c;

@@ -45,8 +45,8 @@ constexpr int A_OCT_B = A_R * ROW_B;               // 2560 B octet pitch of A (=
 constexpr int B_OCT_B = B_R * ROW_B;               // 4608 B octet pitch of B (= LBO)
 constexpr int A_BYTES = KOCT * A_OCT_B;            // 10240
 constexpr int B_BYTES = KOCT * B_OCT_B;            // 18432
-constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);   // hi+lo of both sides = 57344
-constexpr int NSTAGE = 3;
+constexpr int STAGE_BYTES = 2 * A_BYTES + B_BYTES;     // query hi + lo, Ref hi = 38912
+constexpr int NSTAGE = 5;
 constexpr int UM = TQ_R * BW, UN = TR_R * BW;      // 128, 256
 constexpr int TMEM_COLS = 512;
 constexpr int SMEM_AUX = 2 * UN * 8 + 128;         // (scale, bias) per column, double buffered, + barriers
@@ -82,7 +82,6 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap tm_in_hi, const __grid_cons
         tma_prefetch_desc(&tm_in_hi);
         tma_prefetch_desc(&tm_in_lo);
         tma_prefetch_desc(&tm_ref_hi);
-        tma_prefetch_desc(&tm_ref_lo);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < NSTAGE; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -119,7 +118,6 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap tm_in_hi, const __grid_cons
                         tma_load_4d(s, &tm_in_hi, &full[stage], qx0 * 8, qy0, kc * KOCT, b);
                         tma_load_4d(s + A_BYTES, &tm_in_lo, &full[stage], qx0 * 8, qy0, kc * KOCT, b);
                         tma_load_4d(s + 2 * A_BYTES, &tm_ref_hi, &full[stage], rx0 * 8, ry0, kc * KOCT, b);
-                        tma_load_4d(s + 2 * A_BYTES + B_BYTES, &tm_ref_lo, &full[stage], rx0 * 8, ry0, kc * KOCT, b);
                         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -145,16 +143,17 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap tm_in_hi, const __grid_cons
                         const uint64_t dah0 = umma_smem_desc(sa, A_OCT_B, 128);
                         const uint64_t dal0 = umma_smem_desc(sa + A_BYTES, A_OCT_B, 128);
                         const uint64_t dbh0 = umma_smem_desc(sa + 2 * A_BYTES, B_OCT_B, 128);
-                        const uint64_t dbl0 = umma_smem_desc(sa + 2 * A_BYTES + B_BYTES, B_OCT_B, 128);
 #pragma unroll
                         for (int dy = 0; dy < PATCH; ++dy) {
 #pragma unroll
                             for (int j = 0; j < KOCT / 2; ++j) {
                                 const uint32_t ao = dy * ROW_B + j * 2 * A_OCT_B, bo = dy * ROW_B + j * 2 * B_OCT_B;
                                 const uint64_t dah = umma_desc_advance(dah0, ao), dal = umma_desc_advance(dal0, ao);
-                                const uint64_t dbh = umma_desc_advance(dbh0, bo), dbl = umma_desc_advance(dbl0, bo);
+                                const uint64_t dbh = umma_desc_advance(dbh0, bo);
+                                // (q_hi + q_lo) * r_hi: the query keeps its 22-bit split, the Ref operand is its fp16
+                                // rounding.  The search only RANKS; the 2^-11 this costs is part of the rescoring
+                                // window, and a third of the MMAs of the three-product scheme is gone.
                                 umma_f16(d, dah, dbh, idesc, (kc | dy | j) != 0);
-                                umma_f16(d, dah, dbl, idesc, 1);
                                 umma_f16(d, dal, dbh, idesc, 1);
                             }
                         }

@@ -1,11 +1,13 @@
 #!/bin/bash
-# scratch: conv timing after the uniform-datapath MMA issue + parity subset + short bench
-for MODE in psa res; do MODE=$MODE N=9 python tools/conv_one.py 2>&1 | tail -1; done
-H=320 MODE=res N=9 python tools/conv_one.py | tail -1
-H=160 MODE=res N=9 python tools/conv_one.py | tail -1
-H=320 CIN=128 COUT=128 N=9 python tools/conv_one.py | tail -1
-timeout 900 python -m pytest tests -m gpu -q --timeout 600 -p no:cacheprovider -k "conv3x3 or fast_conv or full_forward" 2>&1 | tail -3
-python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-micro 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1])
-print(round(d['value'],1),'img/s', round(d['ms_per_step'],2),'ms', {k:round(v['ms_per_step'],2) for k,v in d['roofline']['per_kernel_class'].items()}, d['clocks'])"
+# scratch: two-product search with top-8 lists: overflow diagnostics, parity, short bench
+O=gpurun_out
+C2M_CORR_DEBUG=1 B=4 STEPS=2 python tools/one_step.py 2>&1 | grep "c2m corr" | tail -2
+T="python -m pytest tests -m gpu -q --timeout 900 -p no:cacheprovider"
+timeout 1200 $T -k "corr or feature_match or search_on or full_forward or fullsize or config2" 2>&1 | tail -4
+python bench.py --steps 10 --warmup 3 --no-micro > $O/r2w_bench.json 2> $O/r2w_bench.err
+python - <<PY
+import json
+d=json.load(open('$O/r2w_bench.json'))
+print(round(d['value'],1),'img/s', round(d['ms_per_step'],2),'ms e2e', round(d['e2e']['value'],1), {k:round(v['ms_per_step'],2) for k,v in d['roofline']['per_kernel_class'].items()}, d['clocks']['sm_mhz'])
+print({k:d['parity'][k] for k in ('idx_flips','max_gap64_of_flips','sr_max_rel_err','psnr_delta_db')})
+PY

@@ -67,7 +67,9 @@ def run_config3(dev, flush, peak_tflops, shapes=((40, 125), (80, 125), (125, 125
         rows.append({'config': 3, 'what': f'feature_match_index 256ch {h}x{h} vs {hr}x{hr}', 'ms_call': ms,
                      'ms_search_kernel': ks, 'algorithmic_tflops_kernel': flops / ks / 1e9,
                      'hbm_gbps_at_algorithmic_bytes_kernel': byts / ks / 1e6,
-                     'frac_of_bf16_peak': flops / ks / 1e9 / peak_tflops, 'algorithmic_mb': byts / 1e6})
+                     'frac_of_bf16_peak': flops / ks / 1e9 / peak_tflops, 'algorithmic_mb': byts / 1e6,
+                     # nine-tap fp32-equivalent flops vs what the kernel issues: 3 row taps x 2 fp16 products x (16/14)^2 halo
+                     'issued_over_algorithmic_mma': round(2.0 / 3.0 * (16.0 / 14.0) ** 2, 3)})
     return rows
 
 
