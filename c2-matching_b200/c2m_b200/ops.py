@@ -327,8 +327,10 @@ def _pack_cached(weight, attr, extra, make):
     cur = torch.cuda.current_stream(weight.device)
     if cached is not None and cached[0] == tag:
         _, blob, ev, st = cached
-        if st != cur.cuda_stream:
-            cur.wait_event(ev)            # packed on another stream: order this stream after the pack kernels
+        if st != cur.cuda_stream and not torch.cuda.is_current_stream_capturing():
+            # packed on another stream: order this stream after the pack kernels.  (A capturing stream cannot wait on
+            # an event recorded outside its capture; RestorationPipeline synchronises the device before it captures.)
+            cur.wait_event(ev)
         return blob
     blob = make()
     ev = torch.cuda.Event()

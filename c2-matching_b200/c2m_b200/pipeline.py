@@ -23,7 +23,7 @@ def synthetic_pair(seed, batch, lr_size, ref_size, device='cpu', generator_devic
 
 class RestorationPipeline:
 
-    def __init__(self, device, ngf=64, n_blocks=16, groups=8, channels_last=False, allow_tf32=False):
+    def __init__(self, device, ngf=64, n_blocks=16, groups=8, channels_last=False, allow_tf32=False, cuda_graph=False):
         self.device = torch.device(device)
         if self.device.type != 'cuda':
             raise RuntimeError('RestorationPipeline needs a CUDA device (no CPU fallback for the B200 hot path)')
@@ -32,6 +32,11 @@ class RestorationPipeline:
         self.net_g = RestorationNet(ngf=ngf, n_blocks=n_blocks, groups=groups)
         self.channels_last = channels_last
         self.allow_tf32 = allow_tf32
+        # cuda_graph: the ~190 launches of a forward are captured once per input shape and replayed (no change in the
+        # arithmetic: bit-identical results; removes the launch gaps between the dependent kernels, ~2 % of a step)
+        self.cuda_graph = bool(cuda_graph)
+        self._graphs = {}
+        self._graph_stream = None
         self._placed = False
 
     def nets(self):
@@ -75,13 +80,64 @@ class RestorationPipeline:
                                '(see c2m_b200.ops.suggest_sa) or the inputs were not finite')
         return (sr, pre_offset.max_idx) if return_idx else sr
 
+    # -- CUDA-graph replay of the forward (opt-in)
+    def _capture(self, shapes, static_in):
+        # two eager passes first (weight packing, scale-exponent calibration, allocator warm-up), then a quiet device
+        torch.cuda.synchronize(self.device)
+        gs = self._graph_stream
+        gs.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(gs):
+            for _ in range(2):
+                self.forward(*static_in)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=gs):
+                static_out = self.forward(*static_in, return_idx=True)
+        torch.cuda.current_stream(self.device).wait_stream(gs)
+        torch.cuda.synchronize(self.device)
+        ent = (g, static_in, static_out)
+        self._graphs[shapes] = ent
+        return ent
+
+    @torch.no_grad()
+    def forward_graphed(self, img_in_lq, img_in_up, img_ref, return_idx=False):
+        """`forward` through a CUDA graph captured per input-shape triple.  The first call for a shape captures (with
+        these inputs as calibration data if nothing ran before); the returned tensors are the graph's static outputs
+        and are overwritten by the next replay of the same shape."""
+        if not self._placed:
+            self.place()
+        shapes = tuple(tuple(t.shape) for t in (img_in_lq, img_in_up, img_ref))
+        ent = self._graphs.get(shapes)
+        if ent is None:
+            static_in = [t.detach().to(self.device, torch.float32).clone() for t in (img_in_lq, img_in_up, img_ref)]
+            if self._graph_stream is None:
+                self._graph_stream = torch.cuda.Stream(self.device)
+            ent = self._capture(shapes, static_in)
+        g, static_in, (sr, idx) = ent
+        for dst, src in zip(static_in, (img_in_lq, img_in_up, img_ref)):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        g.replay()
+        return (sr, idx) if return_idx else sr
+
     @torch.no_grad()
     def run_host(self, img_in_lq, img_in_up, img_ref, out=None):
         """Public end-to-end call: (pinned) HOST tensors in -> HOST SR tensor out; the H2D and
         D2H copies are part of the call."""
         nb = dict(non_blocking=True)
-        sr = self.forward(img_in_lq.to(self.device, **nb), img_in_up.to(self.device, **nb),
-                          img_ref.to(self.device, **nb))
+        if self.cuda_graph:
+            # H2D straight into the graph's static inputs, replay, D2H
+            shapes = tuple(tuple(t.shape) for t in (img_in_lq, img_in_up, img_ref))
+            if shapes not in self._graphs:
+                self.forward_graphed(img_in_lq.to(self.device, **nb), img_in_up.to(self.device, **nb),
+                                     img_ref.to(self.device, **nb))
+            g, static_in, (sr, _) = self._graphs[shapes]
+            for dst, src in zip(static_in, (img_in_lq, img_in_up, img_ref)):
+                dst.copy_(src, non_blocking=True)
+            g.replay()
+        else:
+            sr = self.forward(img_in_lq.to(self.device, **nb), img_in_up.to(self.device, **nb),
+                              img_ref.to(self.device, **nb))
         if out is None:
             out = torch.empty(sr.shape, dtype=sr.dtype, pin_memory=True)
         out.copy_(sr, non_blocking=True)

@@ -620,6 +620,25 @@ def test_full_size_pipeline_is_deterministic_and_batch_invariant():
     assert tuple(sr_a.shape) == (2, 3, 640, 640) and torch.isfinite(sr_a).all()
 
 
+def test_cuda_graph_replay_is_bit_identical_to_eager():
+    """`forward_graphed` / `run_host(cuda_graph=True)`: the forward captured once per input shape and replayed gives exactly
+    the eager results, also for inputs that differ from the ones it was captured with, and for a second shape."""
+    from c2m_b200.pipeline import RestorationPipeline, synthetic_pair
+    pipe = RestorationPipeline(DEV, cuda_graph=True).load_state_dicts(*_weights()).place()
+    first = [t.to(DEV) for t in synthetic_pair(5, 2, 40, 96)]
+    pipe.forward(*first)                                    # calibration happens eagerly, before any capture
+    for seed, batch, lr, rs in ((5, 2, 40, 96), (6, 2, 40, 96), (7, 1, 48, 160), (8, 2, 40, 96)):
+        host = synthetic_pair(seed, batch, lr, rs)
+        x = [t.to(DEV) for t in host]
+        sr_e, idx_e = pipe.forward(*x, return_idx=True)
+        sr_e, idx_e = sr_e.clone(), idx_e.clone()
+        sr_g, idx_g = pipe.forward_graphed(*x, return_idx=True)
+        assert torch.equal(idx_g, idx_e) and torch.equal(sr_g, sr_e), (seed, batch, lr)
+        out = pipe.run_host(*[t.pin_memory() for t in host])
+        assert torch.equal(out, sr_e.cpu())
+    assert len(pipe._graphs) == 2
+
+
 def test_non_square_pipeline_fast_vs_module_path(monkeypatch):
     """CUFED5-like non-square pair (LR 84x124 -> 336x496, Ref 300x420 zero-padded): tcgen05 conv/DCN
     path vs the cuDNN + FFMA module path give the same index map and SR (ragged tiles on every scale)."""
