@@ -320,7 +320,10 @@ int corr_umma_pick_nchunk(const CorrGeom &g, int sms) {
         if (n_eff != n) continue;                      // no empty chunks
         const long long items = (long long)g.B * n_qt * n;
         const double waves = (double)((items + sms - 1) / sms);
-        const double cost = waves * (per + 0.35);
+        // + what the exhaustive re-scan of overflowing (query, chunk) pairs costs: proportional to the chunk length
+        // and to the number of queries (measured on the bench step: 39 entries of 60-tile chunks = 0.86 ms = 2 tile
+        // times per chunk tile at 960 query tiles); also favours more, shorter candidate lists per query
+        const double cost = waves * (per + 0.35) + 2e-3 * (double)g.B * n_qt * per;
         if (cost < best_cost - 1e-9) { best_cost = cost; best_n = n; }
     }
     return best_n;
