@@ -137,6 +137,7 @@ extern "C" int c2m_corr_argmax_f32(const float *fin, const float *fref, int B, i
             return C2M_ERR_UNSUPPORTED;
         }
         ws.nchunk = corr_umma_pick_nchunk(g, sms);
+        if (const char *ev = getenv("C2M_CORR_NCHUNK")) { const int n = atoi(ev); if (n >= 1 && n <= CORR_MAX_CHUNKS) ws.nchunk = n; }   // experiments
         corr_umma_chunk_geom(g, ws.nchunk, cg);
         // the search scores (q_hi + q_lo) . r_hi.  |approx - exact| <= E = [2^-11 + 2^-22 (K/16 + 3)] ||P_q||
         // ||P_r|| rinv_r: 2^-11 = fp16 rounding of the Ref operand (Cauchy-Schwarz over the patch), K/16 tcgen05

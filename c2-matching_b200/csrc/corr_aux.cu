@@ -360,6 +360,31 @@ __device__ __forceinline__ float exact_score_warp(const float *__restrict__ pinb
     return (float)warp_sum(acc);
 }
 
+// fp32 FMA score of (query pixel qp, Ref pixel rp) times the precomputed 1/(||P_r|| + 1e-5), one warp; differs from the
+// exact score by at most E32 = (K + 8) 2^-24 ||P_q|| ||P_r|| rinv_r (K-term FMA chain + the reciprocal instead of the
+// per-element division).  ~1/8 of the instructions of exact_score_warp: a prefilter, never a result.
+__device__ __forceinline__ float fp32_score_warp(const float *__restrict__ pinb, const float *__restrict__ prefb,
+                                                 const CorrGeom &g, int qp, int rp, float rinv_r, int lane) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 3
+    for (int tap = 0; tap < g.patch * g.patch; ++tap) {
+        const int dy = tap / g.patch, dx = tap % g.patch;
+        const float *rrow = prefb + (size_t)(rp + dy * g.wr + dx) * g.Cp;
+        const float *qrow = pinb + (size_t)(qp + dy * g.w + dx) * g.Cp;
+#pragma unroll 2
+        for (int c = lane * 4; c < g.Cp; c += 128) {
+            const float4 rv = *reinterpret_cast<const float4 *>(rrow + c);
+            const float4 qv = *reinterpret_cast<const float4 *>(qrow + c);
+            a0 = fmaf(qv.x, rv.x, a0); a1 = fmaf(qv.y, rv.y, a1);
+            a2 = fmaf(qv.z, rv.z, a2); a3 = fmaf(qv.w, rv.w, a3);
+        }
+    }
+    float s32 = (a0 + a1) + (a2 + a3);
+#pragma unroll
+    for (int of = 16; of; of >>= 1) s32 += __shfl_xor_sync(0xffffffffu, s32, of);
+    return s32 * rinv_r;
+}
+
 __device__ __forceinline__ double query_patch_ss(const float *__restrict__ pinb, const CorrGeom &g, int qp, int lane) {
     double ssq = 0.0;
 #pragma unroll 3
@@ -377,7 +402,8 @@ __device__ __forceinline__ double query_patch_ss(const float *__restrict__ pinb,
 
 __global__ void __launch_bounds__(256) rescore_kernel(const float *__restrict__ pin, const float *__restrict__ pref,
                                                       const Candidate *__restrict__ part, CorrGeom g, int nchunk,
-                                                      float window_coef, const unsigned *__restrict__ max_pn_bits,
+                                                      float window_coef, float e32_coef, const float *__restrict__ rinv,
+                                                      const unsigned *__restrict__ max_pn_bits,
                                                       int is_norm, unsigned long long *__restrict__ best_out,
                                                       float *__restrict__ qnorm, CorrOverflow *__restrict__ ovf,
                                                       unsigned *__restrict__ ovf_count) {
@@ -421,17 +447,38 @@ __global__ void __launch_bounds__(256) rescore_kernel(const float *__restrict__ 
         ovf_mask = __ballot_sync(0xffffffffu, hit);
     }
 
+    // The candidate with the best approximate score is evaluated exactly first (it usually wins); every other in-window
+    // candidate first gets the fp32 FMA score and is skipped when even s32 + E32 stays below the best exact score so far.
+    const float e32 = e32_coef * qn * (is_norm ? 1.f : __uint_as_float(*max_pn_bits)) + 1e-6f;
+    const float *rinvb = rinv + (size_t)b * g.NR;
     float best = -INFINITY;
     int besti = 0x7fffffff;
+    int first_slot = -1;
+#pragma unroll
+    for (int k = 0; k < CORR_TOPK; ++k) {
+        const unsigned top = __ballot_sync(0xffffffffu, ci[k] >= 0 && cv[k] == vmax);
+        if (first_slot < 0 && top) {
+            const int src = __ffs(top) - 1;
+            if (!((ovf_mask >> ((src + 32 * k) / CORR_TOPK)) & 1u)) {
+                const int r = __shfl_sync(0xffffffffu, ci[k], src);
+                const int rp = ((r / g.rw) * g.s_ref) * g.wr + (r % g.rw) * g.s_ref;
+                best = exact_score_warp(pinb, prefb, g, qp, rp, is_norm, lane);
+                besti = r;
+            }
+            first_slot = src + 32 * k;
+        }
+    }
 #pragma unroll
     for (int k = 0; k < CORR_TOPK; ++k) {
         unsigned sel = __ballot_sync(0xffffffffu, ci[k] >= 0 && cv[k] >= thr);
         while (sel) {
             const int src = __ffs(sel) - 1;
             sel &= sel - 1;
+            if (src + 32 * k == first_slot) continue;                             // done above
             const int r = __shfl_sync(0xffffffffu, ci[k], src);
             if ((ovf_mask >> ((src + 32 * k) / CORR_TOPK)) & 1u) continue;      // the re-scan covers this chunk anyway
             const int rp = ((r / g.rw) * g.s_ref) * g.wr + (r % g.rw) * g.s_ref;
+            if (fp32_score_warp(pinb, prefb, g, qp, rp, is_norm ? rinvb[r] : 1.f, lane) < best - e32) continue;
             const float s = exact_score_warp(pinb, prefb, g, qp, rp, is_norm, lane);
             if (cand_better(s, r, best, besti)) { best = s; besti = r; }
         }
@@ -558,8 +605,11 @@ __global__ void __launch_bounds__(256) rescore_finish_kernel(const unsigned long
 int corr_rescore_launch(const CorrGeom &g, const CorrWorkspace &ws, const CorrChunkGeom &cg, float window_coef,
                         int is_norm, int norm_input, int64_t *idx, float *val, cudaStream_t st) {
     dim3 grid(ceil_div(g.NQ, 8), g.B);
-    rescore_kernel<<<grid, 256, 0, st>>>(ws.p32_in, ws.p32_ref, ws.part, g, ws.nchunk, window_coef, ws.max_pn_bits,
-                                         is_norm, ws.best, ws.qnorm, ws.ovf, ws.ovf_count);
+    const int K = g.Cp * g.patch * g.patch;
+    float e32_coef = ldexpf(1.f, -24) * (float)(K + 8);
+    if (const char *ev = getenv("C2M_RESCORE_PREFILTER")) if (atoi(ev) == 0) e32_coef = 1e30f;     // experiment: prefilter never skips
+    rescore_kernel<<<grid, 256, 0, st>>>(ws.p32_in, ws.p32_ref, ws.part, g, ws.nchunk, window_coef, e32_coef, ws.rinv,
+                                         ws.max_pn_bits, is_norm, ws.best, ws.qnorm, ws.ovf, ws.ovf_count);
     C2M_LAUNCH_CHECK("rescore_kernel");
     if (getenv("C2M_CORR_DEBUG")) {                 // diagnostics only: how many (query, chunk-mask) entries overflowed
         unsigned n_ovf = 0;
@@ -574,9 +624,7 @@ int corr_rescore_launch(const CorrGeom &g, const CorrWorkspace &ws, const CorrCh
         for (size_t i = 0; i < h.size() && i < 6; ++i) fprintf(stderr, "   q %d mask %08x\n", h[i].query, h[i].chunks);
     }
     // fp32 prefilter of the re-scan: query patch in shared memory when it fits (it does for every model shape)
-    const int K = g.Cp * g.patch * g.patch;
     const int qs_floats = K * 4 <= 48 * 1024 ? K : 0;
-    const float e32_coef = ldexpf(1.f, -24) * (float)(K + 8);
     rescore_overflow_kernel<<<592, 256, qs_floats * 4, st>>>(ws.p32_in, ws.p32_ref, ws.rinv, g, cg, ws.nchunk, is_norm, e32_coef,
                                                              ws.max_pn_bits, ws.qnorm, qs_floats, ws.ovf, ws.ovf_count, ws.best);
     C2M_LAUNCH_CHECK("rescore_overflow_kernel");

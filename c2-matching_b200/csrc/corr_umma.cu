@@ -320,10 +320,11 @@ int corr_umma_pick_nchunk(const CorrGeom &g, int sms) {
         if (n_eff != n) continue;                      // no empty chunks
         const long long items = (long long)g.B * n_qt * n;
         const double waves = (double)((items + sms - 1) / sms);
-        // + what the exhaustive re-scan of overflowing (query, chunk) pairs costs: proportional to the chunk length
-        // and to the number of queries (measured on the bench step: 39 entries of 60-tile chunks = 0.86 ms = 2 tile
-        // times per chunk tile at 960 query tiles); also favours more, shorter candidate lists per query
-        const double cost = waves * (per + 0.35) + 2e-3 * (double)g.B * n_qt * per;
+        // + what the rescoring side costs per query tile (fitted on the bench step, `profiles/r02_search_chunks.md`):
+        // the exhaustive re-scan of overflowing (query, chunk) pairs grows with the chunk length, and the rescoring
+        // kernel reads the 8 n candidate slots of a query in rounds of 32 (one more round per four chunks)
+        const double q_tiles = (double)g.B * n_qt;
+        const double cost = waves * (per + 0.35) + q_tiles * (2e-3 * per + 0.045 * ((n + 3) / 4 - 1));
         if (cost < best_cost - 1e-9) { best_cost = cost; best_n = n; }
     }
     return best_n;

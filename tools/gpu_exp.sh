@@ -1,13 +1,12 @@
 #!/bin/bash
-# scratch: chunk-count model with the re-scan term: diagnostics, corr parity, bench
-O=gpurun_out
-C2M_CORR_DEBUG=1 B=4 STEPS=2 python tools/one_step.py 2>&1 | grep "c2m corr" | tail -1
-timeout 1200 python -m pytest tests -m gpu -q --timeout 900 -p no:cacheprovider -k "corr or feature_match or search_on or fullsize or config2" 2>&1 | tail -3
-python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $O/r2z_bench.json 2> $O/r2z_bench.err
-python - <<PY
-import json
-d=json.load(open('$O/r2z_bench.json'))
-print(round(d['value'],1),'img/s', round(d['ms_per_step'],2),'ms e2e', round(d['e2e']['value'],1), {k:round(v['ms_per_step'],2) for k,v in d['roofline']['per_kernel_class'].items()}, d['clocks']['sm_mhz'])
-for m in d['micro']['rows'] if 'rows' in d['micro'] else d['micro'].get('results', []):
-    if 'ms_search_kernel' in m: print(m['what'], round(m['ms_call'],3), round(m['ms_search_kernel'],4))
+# scratch: rescore kernel time vs chunk count and prefilter (ncu on the rescore kernels of the bench step)
+for cfg in "2 1" "2 0" "4 1" "10 1" "10 0" "6 1"; do set -- $cfg
+  C2M_CORR_NCHUNK=$1 C2M_RESCORE_PREFILTER=$2 B=4 STEPS=2 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"rescore|corr_umma" --csv --log-file gpurun_out/r3b_$1_$2.csv python tools/one_step.py > /dev/null 2>&1
+  python - <<PY
+import csv
+rows=[r for r in csv.DictReader(l for l in open('gpurun_out/r3b_$1_$2.csv') if not l.startswith('=='))]
+t={}
+for r in rows[len(rows)//2:]: t[r['Kernel Name'].split('(')[0]]=float(r['Metric Value'].replace(',',''))/ (1e6 if r['Metric Unit'] in ('ns','nsecond') else 1e3 if r['Metric Unit'] in ('us','usecond') else 1)
+print('nchunk $1 prefilter $2', {k:round(v,3) for k,v in t.items()}, 'sum', round(sum(t.values()),3))
 PY
+done
