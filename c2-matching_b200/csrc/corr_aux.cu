@@ -459,12 +459,10 @@ __global__ void __launch_bounds__(256) rescore_kernel(const float *__restrict__ 
         const unsigned top = __ballot_sync(0xffffffffu, ci[k] >= 0 && cv[k] == vmax);
         if (first_slot < 0 && top) {
             const int src = __ffs(top) - 1;
-            if (!((ovf_mask >> ((src + 32 * k) / CORR_TOPK)) & 1u)) {
-                const int r = __shfl_sync(0xffffffffu, ci[k], src);
-                const int rp = ((r / g.rw) * g.s_ref) * g.wr + (r % g.rw) * g.s_ref;
-                best = exact_score_warp(pinb, prefb, g, qp, rp, is_norm, lane);
-                besti = r;
-            }
+            const int r = __shfl_sync(0xffffffffu, ci[k], src);
+            const int rp = ((r / g.rw) * g.s_ref) * g.wr + (r % g.rw) * g.s_ref;
+            best = exact_score_warp(pinb, prefb, g, qp, rp, is_norm, lane);
+            besti = r;
             first_slot = src + 32 * k;
         }
     }
@@ -475,8 +473,9 @@ __global__ void __launch_bounds__(256) rescore_kernel(const float *__restrict__ 
             const int src = __ffs(sel) - 1;
             sel &= sel - 1;
             if (src + 32 * k == first_slot) continue;                             // done above
+            // (listed candidates of a flagged chunk are evaluated too: the re-scan may be skipped by its budget, and then
+            // the best LISTED candidate is the result — within 2E of the exact maximum, see corr_rescore_launch)
             const int r = __shfl_sync(0xffffffffu, ci[k], src);
-            if ((ovf_mask >> ((src + 32 * k) / CORR_TOPK)) & 1u) continue;      // the re-scan covers this chunk anyway
             const int rp = ((r / g.rw) * g.s_ref) * g.wr + (r % g.rw) * g.s_ref;
             if (fp32_score_warp(pinb, prefb, g, qp, rp, is_norm ? rinvb[r] : 1.f, lane) < best - e32) continue;
             const float s = exact_score_warp(pinb, prefb, g, qp, rp, is_norm, lane);
@@ -510,11 +509,12 @@ __global__ void __launch_bounds__(256) rescore_overflow_kernel(const float *__re
                                                                const unsigned *__restrict__ max_pn_bits,
                                                                const float *__restrict__ qnorm, int qs_floats,
                                                                const CorrOverflow *__restrict__ ovf,
-                                                               const unsigned *__restrict__ ovf_count,
+                                                               const unsigned *__restrict__ ovf_count, unsigned budget,
                                                                unsigned long long *__restrict__ best_out) {
     extern __shared__ __align__(16) float qs[];          // query patch [taps][Cp] (qs_floats == 0: no prefilter)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned count = *ovf_count;
+    if (count > budget) return;                          // tie-flooded input: see corr_rescore_launch
     const int per_tile = cg.tile_rows * cg.tile_cols;
     const int taps = g.patch * g.patch;
     for (unsigned wi = blockIdx.x; wi < count * OVF_SPLIT; wi += gridDim.x) {
@@ -619,14 +619,25 @@ int corr_rescore_launch(const CorrGeom &g, const CorrWorkspace &ws, const CorrCh
         if (!h.empty()) cudaMemcpy(h.data(), ws.ovf, h.size() * sizeof(CorrOverflow), cudaMemcpyDeviceToHost);
         unsigned long long bits = 0;
         for (auto &e : h) bits += __builtin_popcount(e.chunks);
-        fprintf(stderr, "[c2m corr] queries %d, chunks %d, window_coef %.3e, overflow entries %u, flagged chunks in the first %zu: %llu\n",
-                g.B * g.NQ, ws.nchunk, window_coef, n_ovf, h.size(), bits);
+        fprintf(stderr, "[c2m corr] queries %d, chunks %d, window_coef %.3e, overflow entries %u (re-scan budget %u), flagged chunks in the first %zu: %llu\n",
+                g.B * g.NQ, ws.nchunk, window_coef, n_ovf, (unsigned)(g.B * g.NQ) / 256u < 64u ? 64u : (unsigned)(g.B * g.NQ) / 256u, h.size(), bits);
         for (size_t i = 0; i < h.size() && i < 6; ++i) fprintf(stderr, "   q %d mask %08x\n", h[i].query, h[i].chunks);
     }
     // fp32 prefilter of the re-scan: query patch in shared memory when it fits (it does for every model shape)
     const int qs_floats = K * 4 <= 48 * 1024 ? K : 0;
+    // Budget of the exhaustive pass.  On inputs whose scores are flooded with near-ties (flat or very smooth images: most
+    // Ref patches within the window of most queries) the re-scan degenerates into an exhaustive fp64-exact search — seconds
+    // per batch — to order candidates that differ by less than the reference's own fp32 rounding noise.  When more than
+    // max(64, queries / 256) queries overflow, the pass is skipped for the whole call (a deterministic, data-only decision)
+    // and an overflowed query keeps the exactly-evaluated best of its LISTED candidates.  Every unlisted candidate u of a
+    // chunk has s~(u) <= the chunk's listed maximum <= vmax, and the winner w satisfies s(w) >= s(c*) >= vmax - E for
+    // the listed candidate c* with s~ = vmax (always evaluated), so s(u) - s(w) <= 2E: the result is within 2E (= the
+    // rescoring window) of the exact maximum.  C2M_CORR_EXACT_TIES=1 removes the budget (always exhaustive).
+    unsigned budget = (unsigned)(g.B * g.NQ) / 256u;
+    if (budget < 64u) budget = 64u;
+    if (const char *ev = getenv("C2M_CORR_EXACT_TIES")) if (atoi(ev) != 0) budget = 0xffffffffu;
     rescore_overflow_kernel<<<592, 256, qs_floats * 4, st>>>(ws.p32_in, ws.p32_ref, ws.rinv, g, cg, ws.nchunk, is_norm, e32_coef,
-                                                             ws.max_pn_bits, ws.qnorm, qs_floats, ws.ovf, ws.ovf_count, ws.best);
+                                                             ws.max_pn_bits, ws.qnorm, qs_floats, ws.ovf, ws.ovf_count, budget, ws.best);
     C2M_LAUNCH_CHECK("rescore_overflow_kernel");
     const int n = g.B * g.NQ;
     rescore_finish_kernel<<<ceil_div(n, 256), 256, 0, st>>>(ws.best, ws.qnorm, n, norm_input, idx, val);

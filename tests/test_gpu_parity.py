@@ -117,6 +117,33 @@ def test_corr_full_size_properties():
         assert abs(s - float(val[qy, qx])) < 2e-6
 
 
+def test_corr_tie_flooded_input_budget_and_exact_mode(monkeypatch):
+    """Smooth feature maps put most Ref patches inside every query's rescoring window.  Default: the exhaustive re-scan
+    is skipped once more than max(64, queries / 256) queries overflow, and the result is the best LISTED candidate —
+    within 2E (the window) of the exact maximum.  C2M_CORR_EXACT_TIES=1: always exhaustive = the oracle's argmax."""
+    import c2m_b200 as c2m
+    g = torch.Generator().manual_seed(21)
+    def smooth(c, h, w):
+        base = torch.rand(1, c, 5, 5, generator=g)
+        x = F.interpolate(base, size=(h, w), mode='bicubic', align_corners=False) + 0.002 * torch.randn(1, c, h, w, generator=g)
+        return x[0]
+    fin, fref = smooth(64, 40, 40), smooth(64, 44, 44)
+    idx_b, val_b = c2m.corr_argmax(fin[None].to(DEV), fref[None].to(DEV), norm_input=True)
+    monkeypatch.setenv('C2M_CORR_EXACT_TIES', '1')
+    idx_e, val_e = c2m.corr_argmax(fin[None].to(DEV), fref[None].to(DEV), norm_input=True)
+    monkeypatch.delenv('C2M_CORR_EXACT_TIES')
+    # exact mode against the literal fp64 oracle
+    o_idx, o_val, gap = c_oracle.corr_argmax(fin, fref, is_norm=True, norm_input=True, want_gap=True)
+    bad = idx_e[0].cpu() != o_idx
+    assert int(bad.sum()) == 0 or float(gap[bad].max()) < 1e-6, int(bad.sum())
+    # budget mode: every query's exact score is within the window of the exact maximum (val = score / (||P_q|| + 1e-5))
+    K = 64 * 9
+    window = 1.01 * 2.0 ** -10 + 2.0 ** -20 * (K / 16 + 3)
+    short = (val_e - val_b)[0].cpu()
+    assert float(short.min()) >= -1e-6 and float(short.max()) <= window * 1.01, (float(short.min()), float(short.max()))
+    assert torch.isfinite(val_b).all() and int(idx_b.min()) >= 0 and int(idx_b.max()) < 42 * 42
+
+
 def test_corr_error_paths():
     import c2m_b200 as c2m
     from c2m_b200._lib import C2MError

@@ -36,6 +36,8 @@ xi = ops.psa_interleave(xp)
 back = ops.psa_to_f32(a)
 # a search that overflows its candidate lists (constant features: every score ties) -> exhaustive re-scan kernels
 flat = torch.ones(1, 64, 20, 22, device=dev)
+os.environ['C2M_CORR_EXACT_TIES'] = '1'          # no budget: the exhaustive pass must run under the sanitizer
 c2m.corr_argmax(flat, flat, norm_input=True, l2norm=True)
+os.environ.pop('C2M_CORR_EXACT_TIES')
 torch.cuda.synchronize()
 print('ok', float((y1 - y2).abs().max()), tuple(d.shape), tuple(e.shape))
