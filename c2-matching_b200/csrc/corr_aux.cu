@@ -320,8 +320,8 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // exact score of (query pixel qp, Ref pixel rp), computed by one warp; every lane returns it.  Rows are read
 // as float4 (Cp is a multiple of 8) with the tap / channel loops unrolled so that several loads are in flight.
-__device__ __forceinline__ float exact_score_warp(const float *__restrict__ pinb, const float *__restrict__ prefb,
-                                                  const CorrGeom &g, int qp, int rp, int is_norm, int lane) {
+__device__ __noinline__ float exact_score_warp(const float *__restrict__ pinb, const float *__restrict__ prefb,
+                                               const CorrGeom &g, int qp, int rp, int is_norm, int lane) {
     const int taps = g.patch * g.patch;
     float denom = 1.f;
     if (is_norm) {
@@ -363,8 +363,8 @@ __device__ __forceinline__ float exact_score_warp(const float *__restrict__ pinb
 // fp32 FMA score of (query pixel qp, Ref pixel rp) times the precomputed 1/(||P_r|| + 1e-5), one warp; differs from the
 // exact score by at most E32 = (K + 8) 2^-24 ||P_q|| ||P_r|| rinv_r (K-term FMA chain + the reciprocal instead of the
 // per-element division).  ~1/8 of the instructions of exact_score_warp: a prefilter, never a result.
-__device__ __forceinline__ float fp32_score_warp(const float *__restrict__ pinb, const float *__restrict__ prefb,
-                                                 const CorrGeom &g, int qp, int rp, float rinv_r, int lane) {
+__device__ __noinline__ float fp32_score_warp(const float *__restrict__ pinb, const float *__restrict__ prefb,
+                                              const CorrGeom &g, int qp, int rp, float rinv_r, int lane) {
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 3
     for (int tap = 0; tap < g.patch * g.patch; ++tap) {

@@ -320,11 +320,10 @@ int corr_umma_pick_nchunk(const CorrGeom &g, int sms) {
         if (n_eff != n) continue;                      // no empty chunks
         const long long items = (long long)g.B * n_qt * n;
         const double waves = (double)((items + sms - 1) / sms);
-        // + what the rescoring side costs per query tile (fitted on the bench step, `profiles/r02_search_chunks.md`):
-        // the exhaustive re-scan of overflowing (query, chunk) pairs grows with the chunk length, and the rescoring
-        // kernel reads the 8 n candidate slots of a query in rounds of 32 (one more round per four chunks)
+        // + what the exhaustive re-scan of overflowing (query, chunk) pairs costs per query tile: it grows with the chunk
+        // length (fitted on the bench step, `profiles/r02_search_chunks.md`); shorter chunks also mean more list slots
         const double q_tiles = (double)g.B * n_qt;
-        const double cost = waves * (per + 0.35) + q_tiles * (2e-3 * per + 0.045 * ((n + 3) / 4 - 1));
+        const double cost = waves * (per + 0.35) + q_tiles * 2e-3 * per;
         if (cost < best_cost - 1e-9) { best_cost = cost; best_n = n; }
     }
     return best_n;

@@ -1,11 +1,13 @@
 #!/bin/bash
-timeout 600 python -m pytest tests -m gpu -q --timeout 600 -p no:cacheprovider -k "tie_flooded" 2>&1 | tail -12
-C2M_CORR_DEBUG=1 python - <<'PY' 2>&1 | grep "c2m corr" | tail -2
-import sys; sys.path[:0]=['.','c2-matching_b200','tests/golden']
-import torch, torch.nn.functional as F
-import c2m_b200 as c2m
-g = torch.Generator().manual_seed(21)
-def smooth(c,h,w):
-    base=torch.rand(1,c,5,5,generator=g); return (F.interpolate(base,size=(h,w),mode='bicubic',align_corners=False)+0.002*torch.randn(1,c,h,w,generator=g))
-c2m.corr_argmax(smooth(64,40,40).cuda(), smooth(64,44,44).cuda(), norm_input=True); torch.cuda.synchronize()
+# scratch: rescore kernels after moving the score helpers out of line
+for cfg in "4" "10"; do
+  C2M_CORR_NCHUNK=$cfg B=4 STEPS=2 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"rescore|corr_umma" --csv --log-file gpurun_out/r3f_$cfg.csv python tools/one_step.py > /dev/null 2>&1
+  python - <<PY
+import csv
+rows=[r for r in csv.DictReader(l for l in open('gpurun_out/r3f_$cfg.csv') if not l.startswith('=='))]
+t={}
+for r in rows[len(rows)//2:]: t[r['Kernel Name'].split('(')[0]]=float(r['Metric Value'].replace(',',''))/ (1e6 if r['Metric Unit'] in ('ns','nsecond') else 1e3 if r['Metric Unit'] in ('us','usecond') else 1)
+print('nchunk $cfg', {k:round(v,3) for k,v in t.items()}, 'sum', round(sum(t.values()),3))
 PY
+done
+timeout 1200 python -m pytest tests -m gpu -q --timeout 900 -p no:cacheprovider -k "corr or feature_match or search_on or fullsize or config2" 2>&1 | tail -3
