@@ -103,3 +103,42 @@ def test_shard_indices_cover():
         for w in (1, 2, 4, 8):
             got = sorted(i for r in range(w) for i in shard_indices(n, r, w))
             assert got == list(range(n))
+
+
+def _loader_worker(rank, world, port, q):
+    sys.path.insert(0, os.path.join(ROOT, 'c2-matching_b200'))
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from mmsr.data import create_dataloader, create_dataset
+    opt = {'name': 'synth', 'type': 'SyntheticRefDataset', 'phase': 'test', 'num': 9, 'gt_size': 32, 'ref_size': 24,
+           'scale': 4, 'batch_size': 2, 'num_workers': 1}
+    loader = create_dataloader(create_dataset(opt), opt, dist=True)        # rank / world from the process group
+    names, sizes = [], []
+    for batch in loader:
+        names += list(batch['lq_path'])
+        sizes.append(int(batch['img_in_lq'].shape[0]))
+    loader.close()
+    got = [None] * world
+    dist.all_gather_object(got, (names, sizes))
+    if rank == 0:
+        q.put(got)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_eval_loader_world2():
+    """N1 under an initialised process group: every rank's loader (ShardedEvalSampler -> shape buckets -> PairBatcher with a
+    worker process) decodes only its `rank::world` share; together the ranks cover the pair list exactly once."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29650 + os.getpid() % 200
+    procs = [ctx.Process(target=_loader_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (n0, s0), (n1, s1) = got
+    assert n0 == [f'synthetic_{i:04d}.png' for i in range(0, 9, 2)] and n1 == [f'synthetic_{i:04d}.png' for i in range(1, 9, 2)]
+    assert s0 == [2, 2, 1] and s1 == [2, 2]
