@@ -305,9 +305,9 @@ def run_ours(args, rank, world, local_rank):
                     'hbm_gbps_at_algorithmic_bytes': r['bytes'] / (r['ms'] / 1e3) / 1e9,
                     'issued_over_algorithmic_mma': issued,
                     'note': 'fp32-grade results from fp16 tensor cores: every product is issued as split hi/lo '
-                            'partial products (hi*hi + hi*lo + lo*hi = x3 issued MMA work; the search issues only its '
-                            'row taps as MMAs and sums the column taps in the epilogue), so the tensor-pipe busy '
-                            'fraction is about `issued_over_algorithmic_mma` x `frac`',
+                            'partial products (conv / DCN: hi*hi + hi*lo + lo*hi = x3 issued MMA work; the search issues '
+                            'only its row taps, as the two products (q_hi + q_lo) * r_hi, and sums the column taps in the '
+                            'epilogue), so the tensor-pipe busy fraction is about `issued_over_algorithmic_mma` x `frac`',
                     'per_kernel_class': classes}
         cpu = parity = micro = None
         if world == 1 and not args.no_cpu_baseline:
