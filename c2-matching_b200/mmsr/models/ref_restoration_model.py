@@ -214,6 +214,8 @@ class RefRestorationModel:
                 ev = torch.cuda.Event()
                 ev.record()
                 gts = None if on_gpu else val_data['img_in']
+                if gts is not None and stage is not None:
+                    gts = gts.clone()       # the staging slot is recycled after its H2D copies; the pool reads GT later
                 futs = []
                 for k, meta in enumerate(bmeta):
                     def job(k=k, meta=meta, ev=ev, slot=slot, gts=gts):
