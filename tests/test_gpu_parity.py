@@ -381,9 +381,11 @@ def test_validation_gpu_metrics_equal_host_metrics(tmp_path):
     dset = create_dataset(dopt)
     a = dict(model.validation(create_dataloader(dset, dopt), 0, save_img=True, metrics_device='cuda'))
     b = dict(model.validation(create_dataloader(dset, dict(dopt, per_sample_workers=False)), 0, metrics_device='cpu'))
-    assert a['n'] == b['n'] == 5 and a['metrics_device'] == 'cuda' and b['metrics_device'] == 'cpu'
+    c = dict(model.validation(create_dataloader(dset, dopt), 0, metrics_device='cpu'))     # host metrics behind the PairBatcher
+    assert a['n'] == b['n'] == c['n'] == 5 and a['metrics_device'] == 'cuda' and b['metrics_device'] == 'cpu'
     for k in ('psnr', 'psnr_y', 'ssim_y'):
         assert abs(a[k] - b[k]) <= 1e-9 * max(1.0, abs(b[k])), (k, a[k], b[k])
+        assert c[k] == b[k], (k, c[k], b[k])
     assert len(list((tmp_path / 'synth').glob('*.png'))) == 5
 
 
