@@ -402,3 +402,41 @@ def test_metrics_torch_matches_host_metrics():
     bad = sr.clone()
     bad[1, 5, 5] = float('nan')
     assert metrics_torch.score_image(bad, gt, 4)[3].item() == 0.0
+
+
+def test_two_product_search_rounding_bound():
+    """the tcgen05 search scores (q_hi + q_lo) . r_hi.  The part of its error that does not come from the
+    fp32 accumulation — fp16 rounding of the Ref operand + the query's 22-bit split — stays below
+    [2^-11 + 2^-22] ||P_q|| ||P_r||, also for adversarial operands (values just above a rounding midpoint, all products
+    of one sign).  Emulated in float64, so the accumulation term is absent by construction."""
+    import numpy as np
+    rng = np.random.default_rng(3)
+    K = 2304
+
+    def split(x, s):
+        hi = (x * s).astype(np.float16).astype(np.float64)
+        lo = ((x * s) - hi).astype(np.float16).astype(np.float64)
+        return hi / s, lo / s
+
+    cases = [(rng.standard_normal(K), rng.standard_normal(K)) for _ in range(40)]
+    # adversarial: every Ref element sits just above the midpoint between two fp16 values (relative error -> 2^-11), same sign
+    base = 1.0 + 2.0 ** -11 * (1 + 2 * rng.integers(0, 512, K)) + 1e-7
+    cases.append((np.abs(rng.standard_normal(K)), base * 2.0 ** rng.integers(-6, 3, K)))
+    cases.append((np.ones(K), base))
+    worst = 0.0
+    for q, r in cases:
+        q, r = q.astype(np.float32).astype(np.float64), r.astype(np.float32).astype(np.float64)
+        # operands are scaled by a power of two so that amax lands in the fp16 range, as `sexp_kernel` does
+        sq = 2.0 ** np.floor(np.log2(2.0 ** 14 / np.abs(q).max()))
+        sr = 2.0 ** np.floor(np.log2(2.0 ** 14 / np.abs(r).max()))
+        qh, ql = split(q, sq)
+        rh, _ = split(r, sr)
+        exact = float(np.dot(q, r))
+        approx = float(np.dot(qh + ql, rh))
+        bound = (2.0 ** -11 + 2.0 ** -22) * np.linalg.norm(q) * np.linalg.norm(r)
+        assert abs(approx - exact) <= bound, (abs(approx - exact), bound)
+        worst = max(worst, abs(approx - exact) / bound)
+    assert 0.0 < worst <= 1.0
+    # the window the library uses for K = 2304 (c_abi.cu): 2E for this part, 4E for the accumulation part
+    window_coef = 1.01 * 2.0 ** -10 + 2.0 ** -20 * (K / 16 + 3)
+    assert window_coef >= 2 * (2.0 ** -11 + 2.0 ** -22 * (K / 16 + 3))
